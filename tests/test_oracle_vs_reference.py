@@ -1,0 +1,57 @@
+"""Pin oracle/gpt_oracle.py against the reference's own code (build container only)."""
+import pytest
+import torch
+
+from chattts_b200.prompts import synth_prompt_batch
+from chattts_b200.synth import synth_embed_state, synth_gpt_state
+from oracle.gpt_oracle import GPTOracle, SamplerParams
+
+pytestmark = [pytest.mark.reference]
+
+
+@pytest.fixture(scope="module")
+def models():
+    from oracle.ref_models import build_reference_gpt
+
+    gs, es = synth_gpt_state(0), synth_embed_state(1)
+    gpt, embed = build_reference_gpt(gs, es)
+    return gpt, embed, GPTOracle(gs, es)
+
+
+@pytest.mark.parametrize("lengths,seed", [([16], 1234), ([5, 12, 9], 42)])
+def test_audio_generate_ids_and_hiddens(models, lengths, seed):
+    from oracle.ref_models import reference_generate
+
+    gpt, embed, orc = models
+    ids, mask, tmask = synth_prompt_batch(lengths, seed=1)
+    ref = reference_generate(gpt, embed, ids, mask, tmask, temperature=[0.3] * 4, eos_token=625,
+                             max_new_token=12, min_new_token=12, manual_seed=seed)
+    out = orc.generate(orc.embed_prompt(ids, tmask), ids, torch.tensor([0.3] * 4), 625, attention_mask=mask,
+                       max_new_token=12, min_new_token=12, sampler=SamplerParams(), return_hidden=True,
+                       manual_seed=seed)
+    for b in range(len(lengths)):
+        assert torch.equal(ref.ids[b], out.ids[b]), (b, ref.ids[b], out.ids[b])
+        assert (ref.hiddens[b] - out.hiddens[b]).abs().max() < 2e-5
+
+
+def test_text_generate_ids(models):
+    from oracle.ref_models import reference_generate
+
+    gpt, embed, orc = models
+    ids, mask, tmask = synth_prompt_batch([7, 4], seed=3)
+    ref = reference_generate(gpt, embed, ids, mask, tmask, temperature=[0.7], eos_token=21001, max_new_token=6,
+                             repetition_penalty=1.0, num_code=21178, infer_text=True, return_hidden=False,
+                             manual_seed=7)
+    out = orc.generate(orc.embed_prompt(ids, tmask), ids, torch.tensor([0.7]), 21001, attention_mask=mask,
+                       max_new_token=6, sampler=SamplerParams(repetition_penalty=1.0, penalty_max_ids=21178),
+                       infer_text=True, manual_seed=7)
+    for b in range(2):
+        assert torch.equal(ref.ids[b], out.ids[b])
+
+
+def test_embed_prompt_matches(models):
+    gpt, embed, orc = models
+    ids, mask, tmask = synth_prompt_batch([6, 3], seed=5)
+    tmask[0, -2:] = False  # mixed text / code positions (audio prompt splice, tokenizer.py:115-124)
+    ids[0, -2:] = torch.randint(0, 626, (2, 4))
+    assert torch.equal(embed(ids, tmask), orc.embed_prompt(ids, tmask))
