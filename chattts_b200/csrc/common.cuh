@@ -1,0 +1,94 @@
+// Shared device/host helpers for the chattts_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+
+#include "../../include/chattts_b200.h"
+
+namespace ctb {
+
+extern thread_local char g_err[512];
+extern std::atomic<uint64_t> g_launches;
+
+int set_err(int code, const char* fmt, ...);
+
+#define CTB_CUDA(expr)                                                                      \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess)                                                                  \
+      return ::ctb::set_err(CTB_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr,      \
+                            cudaGetErrorString(_e));                                        \
+  } while (0)
+
+#define CTB_LAUNCH_CHECK()                                                                  \
+  do {                                                                                      \
+    ::ctb::g_launches.fetch_add(1, std::memory_order_relaxed);                              \
+    cudaError_t _e = cudaPeekAtLastError();                                                 \
+    if (_e != cudaSuccess)                                                                  \
+      return ::ctb::set_err(CTB_ERR_CUDA, "%s:%d launch -> %s", __FILE__, __LINE__,         \
+                            cudaGetErrorString(_e));                                        \
+  } while (0)
+
+constexpr int kPageTokens = 16;  // KV page = 16 tokens (the reference's vLLM fork: velocity/configs.py:567)
+
+// ---------------------------------------------------------------- device helpers
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+  // weights / KV are read exactly once per step: bypass L1, keep L2 for activations
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Butterfly reduce-scatter: N per-lane partial values (N = power of two <= 32) are summed
+// across the 32 lanes; afterwards v[0] of lane l holds the total of value (l >> (5 - log2 N)).
+// 31 shuffles for N = 32 instead of 160 for 32 independent all-reduces.
+template <int N>
+__device__ __forceinline__ void warp_reduce_scatter(float (&v)[N]) {
+  const int lane = threadIdx.x & 31;
+  int off = 16;
+#pragma unroll
+  for (int n = N; n > 1; n >>= 1, off >>= 1) {
+    const bool hi = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) {
+      float send = hi ? v[i] : v[i + n / 2];
+      float keep = hi ? v[i + n / 2] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  for (; off > 0; off >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+}
+
+// order-preserving map float -> uint32 (larger float => larger key; -inf smallest)
+__device__ __forceinline__ uint32_t float_key(float f) {
+  uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_float(uint32_t k) {
+  uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+  return __uint_as_float(u);
+}
+
+}  // namespace ctb

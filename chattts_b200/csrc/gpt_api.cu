@@ -1,0 +1,359 @@
+// extern "C" entry points for hot path 1 (see include/chattts_b200.h).
+#include <stdarg.h>
+
+#include <vector>
+
+#define CTB_GPT_KERNELS_IMPL
+#include "gpt_kernels.cuh"
+
+namespace ctb {
+
+thread_local char g_err[512] = {0};
+std::atomic<uint64_t> g_launches{0};
+
+int set_err(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+static int bt_for(int B) {
+  int bt = 1;
+  while (bt < B && bt < 32) bt <<= 1;
+  return bt;
+}
+
+}  // namespace ctb
+
+using namespace ctb;
+
+struct ctb_gpt {
+  ctb_gpt_config cfg;
+  ctb_gpt_layout lay;
+  const float* W;
+  int pages_per_row, nsplit_max, bpad_max;
+  // device state
+  float *x, *qbuf, *attn, *mlp, *logits, *kv, *part;
+  int *block_table, *seq_len, *pos, *counter, *end_idx;
+  int32_t* idx;
+  uint8_t *active, *finish;
+  LoopState* st;
+  size_t kv_layer_floats;
+  // per generate() call
+  int B, T0, max_new, infer_text, started;
+  ctb_sampler_config sampler;
+  const float* q_noise;
+  const float* emb;
+  const uint8_t* mask;
+  int32_t* ids_out;
+  float* hiddens_out;
+  cudaGraphExec_t graph_exec;
+  bool use_graph;
+};
+
+extern "C" int ctb_abi_version(void) { return CTB_ABI_VERSION; }
+extern "C" const char* ctb_last_error(void) { return g_err; }
+extern "C" uint64_t ctb_launch_count(void) { return g_launches.load(); }
+
+extern "C" int ctb_gpt_layout_query(const ctb_gpt_config* c, ctb_gpt_layout* o) {
+  if (!c || !o) return set_err(CTB_ERR_ARG, "null argument");
+  const int64_t d = c->hidden_size, I = c->intermediate_size, hd = c->head_dim;
+  const int64_t nq = (int64_t)c->num_heads * hd, nkv = (int64_t)c->num_kv_heads * hd;
+  int64_t off = 0;
+  o->wqkv = off; off += (nq + 2 * nkv) * d;
+  o->wo = off; off += d * nq;
+  o->wgate_up = off; off += 2 * I * d;
+  o->wdown = off; off += d * I;
+  o->ln1 = off; off += d;
+  o->ln2 = off; off += d;
+  o->layer_stride = off;
+  o->layer0 = 0;
+  off = o->layer_stride * c->num_layers;
+  o->final_norm = off; off += d;
+  o->head_code = off; off += (int64_t)c->num_vq * c->num_audio_tokens * d;
+  o->head_text = off; off += (int64_t)c->num_text_tokens * d;
+  o->emb_code = off; off += (int64_t)c->num_vq * c->num_audio_tokens * d;
+  o->emb_text = off; off += (int64_t)c->num_text_tokens * d;
+  o->rope_cos = off; off += (int64_t)c->max_positions * hd;
+  o->rope_sin = off; off += (int64_t)c->max_positions * hd;
+  o->total = off;
+  return CTB_OK;
+}
+
+template <typename T>
+static int dalloc(T** p, size_t n) {
+  CTB_CUDA(cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T)));
+  CTB_CUDA(cudaMemset(*p, 0, n * sizeof(T)));
+  return CTB_OK;
+}
+
+extern "C" int ctb_gpt_create(const ctb_gpt_config* c, const float* weights_dev, ctb_gpt** out) {
+  if (!c || !weights_dev || !out) return set_err(CTB_ERR_ARG, "null argument");
+  if (c->hidden_size != KC) return set_err(CTB_ERR_ARG, "hidden_size must be %d", KC);
+  if (c->intermediate_size % KC) return set_err(CTB_ERR_ARG, "intermediate_size must be a multiple of %d", KC);
+  if (c->head_dim != 64) return set_err(CTB_ERR_ARG, "head_dim must be 64");
+  if (c->num_heads % c->num_kv_heads) return set_err(CTB_ERR_ARG, "num_heads %% num_kv_heads != 0");
+  if (c->num_vq > 8 || c->num_vq < 1) return set_err(CTB_ERR_ARG, "num_vq out of range");
+  if (c->max_batch < 1 || c->max_context < 1 || c->max_context > c->max_positions)
+    return set_err(CTB_ERR_ARG, "bad max_batch/max_context");
+  int dev_count = 0;
+  CTB_CUDA(cudaGetDeviceCount(&dev_count));
+  if (dev_count < 1) return set_err(CTB_ERR_CUDA, "no CUDA device: chattts_b200 has no CPU path");
+  ctb_gpt* h = new ctb_gpt();
+  memset(h, 0, sizeof(*h));
+  h->cfg = *c;
+  ctb_gpt_layout_query(c, &h->lay);
+  h->W = weights_dev;
+  h->pages_per_row = (c->max_context + kPageTokens - 1) / kPageTokens;
+  h->nsplit_max = (c->max_context + ATT_CHUNK - 1) / ATT_CHUNK;
+  const int bt = bt_for(c->max_batch);
+  h->bpad_max = ((c->max_batch + bt - 1) / bt) * bt;
+  const size_t Bp = h->bpad_max, d = c->hidden_size;
+  const size_t nq = (size_t)c->num_heads * c->head_dim;
+  int rc;
+#define TRY(e) if ((rc = (e)) != CTB_OK) { ctb_gpt_destroy(h); return rc; }
+  TRY(dalloc(&h->x, Bp * d));
+  TRY(dalloc(&h->qbuf, Bp * nq));
+  TRY(dalloc(&h->attn, Bp * nq));
+  TRY(dalloc(&h->mlp, Bp * c->intermediate_size));
+  const size_t nlog = std::max((size_t)c->num_vq * c->num_audio_tokens, (size_t)c->num_text_tokens);
+  TRY(dalloc(&h->logits, Bp * nlog));
+  h->kv_layer_floats = (size_t)c->max_batch * h->pages_per_row * 2 * c->num_kv_heads * kPageTokens * c->head_dim;
+  TRY(dalloc(&h->kv, h->kv_layer_floats * c->num_layers));
+  TRY(dalloc(&h->part, (size_t)c->max_batch * c->num_heads * h->nsplit_max * (c->head_dim + 2)));
+  TRY(dalloc(&h->block_table, (size_t)c->max_batch * h->pages_per_row));
+  TRY(dalloc(&h->seq_len, Bp));
+  TRY(dalloc(&h->pos, Bp));
+  TRY(dalloc(&h->counter, (size_t)c->max_batch * c->num_heads));
+  TRY(dalloc(&h->end_idx, Bp));
+  TRY(dalloc(&h->idx, Bp * c->num_vq));
+  TRY(dalloc(&h->active, Bp));
+  TRY(dalloc(&h->finish, Bp));
+  TRY(dalloc(&h->st, 1));
+#undef TRY
+  // static page assignment: row b owns pages [b*ppr, (b+1)*ppr); kernels only see the table
+  std::vector<int> bt_host((size_t)c->max_batch * h->pages_per_row);
+  for (size_t i = 0; i < bt_host.size(); ++i) bt_host[i] = (int)i;
+  cudaMemcpy(h->block_table, bt_host.data(), bt_host.size() * sizeof(int), cudaMemcpyHostToDevice);
+  h->use_graph = getenv("CTB_NO_GRAPH") == nullptr;
+  *out = h;
+  return CTB_OK;
+}
+
+extern "C" int ctb_gpt_destroy(ctb_gpt* h) {
+  if (!h) return CTB_OK;
+  if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+  void* ptrs[] = {h->x, h->qbuf, h->attn, h->mlp, h->logits, h->kv, h->part, h->block_table, h->seq_len,
+                  h->pos, h->counter, h->end_idx, h->idx, h->active, h->finish, h->st};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  delete h;
+  return CTB_OK;
+}
+
+// ------------------------------------------------------------------ launches
+template <int BT, int EPI>
+static int launch_gemv_t(const GemvP& p, int ntiles, cudaStream_t s) {
+  const size_t smem = (size_t)BT * KC * sizeof(float);
+  static bool attr_done = false;  // per instantiation
+  if (!attr_done) {
+    CTB_CUDA(cudaFuncSetAttribute(k_gemv<BT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  dim3 grid((p.ntasks + GEMV_WARPS - 1) / GEMV_WARPS, ntiles);
+  k_gemv<BT, EPI><<<grid, GEMV_WARPS * 32, smem, s>>>(p);
+  CTB_LAUNCH_CHECK();
+  return CTB_OK;
+}
+
+template <int EPI>
+static int launch_gemv(int bt, const GemvP& p, int ntiles, cudaStream_t s) {
+  switch (bt) {
+    case 1: return launch_gemv_t<1, EPI>(p, ntiles, s);
+    case 2: return launch_gemv_t<2, EPI>(p, ntiles, s);
+    case 4: return launch_gemv_t<4, EPI>(p, ntiles, s);
+    case 8: return launch_gemv_t<8, EPI>(p, ntiles, s);
+    case 16: return launch_gemv_t<16, EPI>(p, ntiles, s);
+    default: return launch_gemv_t<32, EPI>(p, ntiles, s);
+  }
+}
+
+static int launch_sample(const SampleP& sp, cudaStream_t s) {
+  const size_t smem = (size_t)sp.V * sizeof(float) + 1024 * sizeof(uint32_t);
+  static size_t attr_max = 0;
+  if (smem > attr_max) {
+    CTB_CUDA(cudaFuncSetAttribute(k_sample, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_max = smem;
+  }
+  k_sample<<<sp.rows, SAMPLE_THREADS, smem, s>>>(sp);
+  CTB_LAUNCH_CHECK();
+  return CTB_OK;
+}
+
+// One loop iteration.  col >= 0: prefill column `col` of the prompt; col < 0: decode step.
+// sample: run heads + sampler + finalize (last prompt column and every decode step).
+static int enqueue_step(ctb_gpt* h, int col, bool sample, cudaStream_t s) {
+  const ctb_gpt_config& c = h->cfg;
+  const ctb_gpt_layout& L = h->lay;
+  const int B = h->B, bt = bt_for(B), ntiles = (B + bt - 1) / bt;
+  const int decode = col < 0;
+  const int d = c.hidden_size, I = c.intermediate_size, hd = c.head_dim;
+  int rc;
+
+  InputP ip{};
+  ip.st = h->st; ip.decode = decode; ip.B = B; ip.d = d; ip.col = decode ? 0 : col; ip.T0 = h->T0;
+  ip.emb = h->emb; ip.mask = h->mask;
+  ip.emb_code = h->W + L.emb_code; ip.emb_text = h->W + L.emb_text;
+  ip.ids_out = h->ids_out; ip.max_new = h->max_new; ip.num_vq = c.num_vq; ip.num_audio = c.num_audio_tokens;
+  ip.infer_text = h->infer_text;
+  ip.x = h->x; ip.seq_len = h->seq_len; ip.pos = h->pos; ip.active = h->active;
+  k_input<<<B, 256, 0, s>>>(ip);
+  CTB_LAUNCH_CHECK();
+
+  GemvP g{};
+  g.B = B; g.st = h->st; g.check_finished = decode; g.eps = c.rms_eps;
+  g.block_table = h->block_table; g.pages_per_row = h->pages_per_row; g.pos = h->pos; g.active = h->active;
+  g.rope_cos = h->W + L.rope_cos; g.rope_sin = h->W + L.rope_sin;
+  g.Hq = c.num_heads; g.Hkv = c.num_kv_heads; g.hd = hd; g.I = I; g.xres = h->x;
+
+  AttnP a{};
+  a.st = h->st; a.check_finished = decode; a.q = h->qbuf; a.block_table = h->block_table;
+  a.pages_per_row = h->pages_per_row; a.pos = h->pos; a.active = h->active; a.out = h->attn; a.part = h->part;
+  a.counter = h->counter; a.Hq = c.num_heads; a.Hkv = c.num_kv_heads; a.hd = hd; a.nsplit_max = h->nsplit_max;
+  a.scaling = 1.0f / sqrtf((float)hd);
+
+  for (int l = 0; l < c.num_layers; ++l) {
+    const float* Wl = h->W + L.layer0 + (int64_t)l * L.layer_stride;
+    float* kvl = h->kv + (size_t)l * h->kv_layer_floats;
+    GemvP q = g;
+    q.W = Wl + L.wqkv; q.K = d; q.nrows = (c.num_heads + 2 * c.num_kv_heads) * hd; q.ntasks = q.nrows / 2;
+    q.xin = h->x; q.normw = Wl + L.ln1; q.out = h->qbuf; q.kv = kvl;
+    if ((rc = launch_gemv<EPI_QKV>(bt, q, ntiles, s))) return rc;
+
+    a.kv = kvl;
+    // context after this step <= T0 + max_new; only launch the splits that can be populated
+    const int max_ctx = std::min(c.max_context, h->T0 + h->max_new);
+    dim3 agrid((max_ctx + ATT_CHUNK - 1) / ATT_CHUNK, c.num_heads, B);
+    k_attn<<<agrid, ATT_THREADS, 0, s>>>(a);
+    CTB_LAUNCH_CHECK();
+
+    GemvP o = g;
+    o.W = Wl + L.wo; o.K = c.num_heads * hd; o.nrows = d; o.ntasks = d / 2; o.xin = h->attn; o.normw = nullptr;
+    if ((rc = launch_gemv<EPI_OPROJ>(bt, o, ntiles, s))) return rc;
+
+    GemvP gu = g;
+    gu.W = Wl + L.wgate_up; gu.K = d; gu.nrows = 2 * I; gu.ntasks = I; gu.xin = h->x; gu.normw = Wl + L.ln2;
+    gu.out = h->mlp;
+    if ((rc = launch_gemv<EPI_GATEUP>(bt, gu, ntiles, s))) return rc;
+
+    GemvP dn = g;
+    dn.W = Wl + L.wdown; dn.K = I; dn.nrows = d; dn.ntasks = d / 2; dn.xin = h->mlp; dn.normw = nullptr;
+    if ((rc = launch_gemv<EPI_DOWN>(bt, dn, ntiles, s))) return rc;
+  }
+  if (!sample) return CTB_OK;
+
+  const int rpi = h->infer_text ? 1 : c.num_vq;
+  const int V = h->infer_text ? c.num_text_tokens : c.num_audio_tokens;
+  GemvP hp = g;
+  hp.W = h->W + (h->infer_text ? L.head_text : L.head_code);
+  hp.K = d; hp.nrows = rpi * V; hp.ntasks = (hp.nrows + 1) / 2; hp.xin = h->x; hp.normw = h->W + L.final_norm;
+  hp.out = h->logits; hp.rows_per_item = rpi; hp.V = V;
+  hp.hidden_out = h->hiddens_out; hp.hidden_stride = h->max_new * d;
+  if ((rc = launch_gemv<EPI_HEADS>(bt, hp, ntiles, s))) return rc;
+
+  SampleP sp{};
+  sp.st = h->st; sp.check_finished = decode; sp.logits = h->logits; sp.rows = B * rpi; sp.V = V;
+  sp.rows_per_item = rpi; sp.cfg = h->sampler; sp.q_noise = h->q_noise; sp.gen_ids = h->ids_out;
+  sp.gen_stride = h->max_new; sp.gen_inner = c.num_vq; sp.out_idx = h->idx;
+  if ((rc = launch_sample(sp, s))) return rc;
+
+  FinalP fp{};
+  fp.st = h->st; fp.B = B; fp.rows_per_item = rpi; fp.num_vq = c.num_vq; fp.max_new = h->max_new;
+  fp.eos = h->sampler.eos_token; fp.idx = h->idx; fp.ids_out = h->ids_out; fp.finish = h->finish; fp.end_idx = h->end_idx;
+  k_finalize<<<1, 256, 0, s>>>(fp);
+  CTB_LAUNCH_CHECK();
+  return CTB_OK;
+}
+
+extern "C" int ctb_gpt_begin(ctb_gpt* h, int32_t B, int32_t T0, const float* emb_dev, const uint8_t* mask_dev,
+                             const ctb_sampler_config* sampler, const float* q_noise_dev, int32_t max_new_token,
+                             int32_t infer_text, int32_t* ids_out_dev, float* hiddens_out_dev, void* stream) {
+  if (!h || !emb_dev || !mask_dev || !sampler || !ids_out_dev) return set_err(CTB_ERR_ARG, "null argument");
+  if (B < 1 || B > h->cfg.max_batch) return set_err(CTB_ERR_ARG, "B=%d outside [1,%d]", B, h->cfg.max_batch);
+  if (T0 < 1 || max_new_token < 1 || T0 + max_new_token > h->cfg.max_context)
+    return set_err(CTB_ERR_ARG, "T0=%d + max_new=%d exceeds max_context=%d", T0, max_new_token, h->cfg.max_context);
+  if (sampler->past_window > 31 || sampler->past_window < 0) return set_err(CTB_ERR_ARG, "past_window out of range");
+  cudaStream_t s = (cudaStream_t)stream;
+  h->B = B; h->T0 = T0; h->max_new = max_new_token; h->infer_text = infer_text ? 1 : 0;
+  h->sampler = *sampler; h->q_noise = q_noise_dev; h->emb = emb_dev; h->mask = mask_dev;
+  h->ids_out = ids_out_dev; h->hiddens_out = hiddens_out_dev;
+  if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+  CTB_CUDA(cudaMemsetAsync(h->st, 0, sizeof(LoopState), s));
+  CTB_CUDA(cudaMemsetAsync(h->seq_len, 0, sizeof(int) * h->bpad_max, s));
+  CTB_CUDA(cudaMemsetAsync(h->finish, 0, h->bpad_max, s));
+  CTB_CUDA(cudaMemsetAsync(h->end_idx, 0, sizeof(int) * h->bpad_max, s));
+  CTB_CUDA(cudaMemsetAsync(h->counter, 0, sizeof(int) * h->cfg.max_batch * h->cfg.num_heads, s));
+  int rc;
+  // prefill: the prompt is walked column by column through the decode kernels (left padding
+  // keeps every row's last prompt token in the last column, like the reference's batches)
+  for (int col = 0; col < T0; ++col)
+    if ((rc = enqueue_step(h, col, col == T0 - 1, s))) return rc;
+  h->started = 1;
+  return CTB_OK;
+}
+
+extern "C" int ctb_gpt_decode(ctb_gpt* h, int32_t n_steps, void* stream) {
+  if (!h || !h->started) return set_err(CTB_ERR_STATE, "ctb_gpt_begin has not been called");
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc;
+  if (h->use_graph && !h->graph_exec) {
+    cudaGraph_t graph;
+    CTB_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    rc = enqueue_step(h, -1, true, s);
+    cudaError_t e = cudaStreamEndCapture(s, &graph);
+    if (rc) return rc;
+    if (e != cudaSuccess) return set_err(CTB_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+    CTB_CUDA(cudaGraphInstantiate(&h->graph_exec, graph, 0));
+    cudaGraphDestroy(graph);
+  }
+  for (int i = 0; i < n_steps; ++i) {
+    if (h->graph_exec) {
+      CTB_CUDA(cudaGraphLaunch(h->graph_exec, s));
+      g_launches.fetch_add(5 * h->cfg.num_layers + 4, std::memory_order_relaxed);
+    } else if ((rc = enqueue_step(h, -1, true, s))) {
+      return rc;
+    }
+  }
+  return CTB_OK;
+}
+
+extern "C" int ctb_gpt_status_query(ctb_gpt* h, ctb_gpt_status* out, int32_t* end_idx_host, uint8_t* finish_host,
+                                    void* stream) {
+  if (!h || !out) return set_err(CTB_ERR_ARG, "null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  LoopState st;
+  CTB_CUDA(cudaMemcpyAsync(&st, h->st, sizeof(st), cudaMemcpyDeviceToHost, s));
+  if (end_idx_host) CTB_CUDA(cudaMemcpyAsync(end_idx_host, h->end_idx, sizeof(int) * h->B, cudaMemcpyDeviceToHost, s));
+  if (finish_host) CTB_CUDA(cudaMemcpyAsync(finish_host, h->finish, h->B, cudaMemcpyDeviceToHost, s));
+  CTB_CUDA(cudaStreamSynchronize(s));
+  out->steps_done = st.step;
+  out->all_finished = st.all_finished;
+  out->any_finished_first_step = st.any_first;
+  out->reserved = 0;
+  return CTB_OK;
+}
+
+extern "C" int ctb_sample(const float* logits_dev, int32_t rows, int32_t V, int32_t rows_per_item,
+                          const ctb_sampler_config* sampler, const float* q_noise_dev, const int32_t* gen_ids_dev,
+                          int32_t gen_stride, int32_t n_gen, int32_t step, int32_t* out_idx_dev, void* stream) {
+  if (!logits_dev || !sampler || !out_idx_dev) return set_err(CTB_ERR_ARG, "null argument");
+  if (rows < 1 || V < 1 || rows_per_item < 1 || rows % rows_per_item) return set_err(CTB_ERR_ARG, "bad shape");
+  if ((size_t)V * 4 + 4096 > 200 * 1024) return set_err(CTB_ERR_ARG, "V=%d too large for the sampler", V);
+  if (sampler->penalty_on && n_gen > 0 && !gen_ids_dev) return set_err(CTB_ERR_ARG, "gen_ids required");
+  SampleP sp{};
+  sp.st = nullptr; sp.check_finished = 0; sp.logits = logits_dev; sp.rows = rows; sp.V = V;
+  sp.rows_per_item = rows_per_item; sp.cfg = *sampler; sp.q_noise = q_noise_dev; sp.gen_ids = gen_ids_dev;
+  sp.gen_stride = gen_stride; sp.gen_inner = rows_per_item; sp.n_gen_fixed = n_gen; sp.step_fixed = step; sp.out_idx = out_idx_dev;
+  return launch_sample(sp, (cudaStream_t)stream);
+}

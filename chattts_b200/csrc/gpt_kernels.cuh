@@ -1,0 +1,411 @@
+// Decode-step kernels for hot path 1 (GPT.generate, reference ChatTTS/model/gpt.py:394-596).
+//
+// One "step" = k_input -> 20 x [k_gemv<QKV> -> k_attn -> k_gemv<OPROJ> -> k_gemv<GATEUP> -> k_gemv<DOWN>]
+//            -> k_gemv<HEADS> -> k_sample -> k_finalize.
+// All loop state (positions, finish flags, step counter) lives in device memory so a captured
+// CUDA graph of one step can be replayed without host involvement.
+//
+// Numerics: fp32 weights, fp32 FMA accumulation everywhere.  The parity target is the fp32 CPU
+// reference (SURVEY.md 7 "hard parts"): sampled ids must match, so no reduced precision here.
+#pragma once
+#include "common.cuh"
+
+namespace ctb {
+
+struct LoopState {
+  int step;            // loop iterations completed (gpt.py: i)
+  int all_finished;    // finish.all()
+  int any_first;       // i == 0 and finish.any()
+  int n_gen;           // tokens appended to ids_out so far
+};
+
+constexpr int KC = 768;        // K chunk staged in shared memory (= hidden size of the model)
+constexpr int GEMV_WARPS = 8;  // warps per CTA, one 2-row task per warp
+constexpr int ATT_CHUNK = 128; // tokens per attention CTA (flash-decoding split)
+constexpr int ATT_THREADS = 128;
+
+enum Epi { EPI_QKV = 0, EPI_OPROJ = 1, EPI_GATEUP = 2, EPI_DOWN = 3, EPI_HEADS = 4 };
+
+struct GemvP {
+  const float* W;        // [rows, K] row-major
+  int K;                 // 768 or a multiple of 768
+  int ntasks;            // 2-row warp tasks
+  int nrows;             // valid rows of W
+  const float* xin;      // [Bpad, K]
+  const float* normw;    // RMSNorm weight (prologue) or nullptr
+  float eps;
+  int B;                 // real batch rows
+  const LoopState* st;   // nullptr: never skip
+  int check_finished;    // decode steps early-exit once all rows finished
+  // --- epilogue targets
+  float* xres;           // residual stream [Bpad, d]   (OPROJ / DOWN: +=)
+  float* out;            // GATEUP: mlp [Bpad, I]; HEADS: logits; QKV: q buffer [Bpad, Hq*hd]
+  float* kv;             // QKV: KV pool of this layer
+  const int* block_table;
+  int pages_per_row;
+  const int* pos;        // [Bpad] position of the current token per row
+  const uint8_t* active; // [Bpad]
+  const float* rope_cos; // [max_pos, hd]
+  const float* rope_sin;
+  int Hq, Hkv, hd, I;
+  // HEADS
+  int rows_per_item;     // num_vq (audio) or 1 (text)
+  int V;
+  float* hidden_out;     // [B, max_new, d] or nullptr
+  int hidden_stride;     // max_new * d
+};
+
+// KV pool layout of one layer: [page][2 (K,V)][Hkv][16 tokens][hd]
+__device__ __forceinline__ size_t kv_off(int page, int which, int h, int slot, int Hkv, int hd) {
+  return ((((size_t)page * 2 + which) * Hkv + h) * kPageTokens + slot) * hd;
+}
+
+template <int BT, int EPI>
+__global__ void __launch_bounds__(GEMV_WARPS * 32) k_gemv(const GemvP p) {
+  if (p.check_finished && p.st->all_finished) return;
+  extern __shared__ __align__(16) float xs[];  // [BT][KC]
+  __shared__ float rinv[BT];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int task = blockIdx.x * GEMV_WARPS + warp;
+  const bool has_task = task < p.ntasks;
+  const int bbase = blockIdx.y * BT;        // batch tile (B > 32 re-streams the weights per tile)
+  const int nb = min(BT, p.B - bbase);      // live rows in this tile
+
+  // ---- rows of this warp's task
+  int r0 = 0, r1 = 0;
+  if (EPI == EPI_QKV) {
+    // task -> (which, head, j): rows j and j+32 of one head so RoPE pairs stay in-warp
+    const int half = p.hd / 2;
+    int t = task, base = 0, which = 0;
+    const int nq = p.Hq * half, nk = p.Hkv * half;
+    if (t >= nq + nk) { which = 2; t -= nq + nk; base = (p.Hq + p.Hkv) * p.hd; }
+    else if (t >= nq) { which = 1; t -= nq; base = p.Hq * p.hd; }
+    (void)which;
+    r0 = base + (t / half) * p.hd + (t % half);
+    r1 = r0 + half;
+  } else if (EPI == EPI_GATEUP) {
+    r0 = task; r1 = p.I + task;
+  } else {
+    r0 = 2 * task; r1 = 2 * task + 1;
+  }
+  const bool r1_valid = r1 < p.nrows;
+  if (!r1_valid) r1 = r0;
+
+  float acc0[BT], acc1[BT];
+#pragma unroll
+  for (int b = 0; b < BT; ++b) { acc0[b] = 0.f; acc1[b] = 0.f; }
+
+  const int nchunks = p.K / KC;
+  const float4* w0p = reinterpret_cast<const float4*>(p.W + (size_t)r0 * p.K) + lane;
+  const float4* w1p = reinterpret_cast<const float4*>(p.W + (size_t)r1 * p.K) + lane;
+
+  // issue the first chunk's weight loads before touching activations: they do not depend on
+  // the previous kernel and hide the prologue latency
+  float4 w0[6], w1[6];
+  if (has_task) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { w0[i] = ldg_stream(w0p + i * 32); w1[i] = ldg_stream(w1p + i * 32); }
+  }
+
+  for (int c = 0; c < nchunks; ++c) {
+    if (c > 0) __syncthreads();
+    // ---- stage activations [BT][KC] (zero rows beyond B)
+    for (int i = tid; i < BT * (KC / 4); i += GEMV_WARPS * 32) {
+      const int b = i / (KC / 4), k4 = i % (KC / 4);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (b < nb) v = *reinterpret_cast<const float4*>(p.xin + (size_t)(bbase + b) * p.K + c * KC + k4 * 4);
+      reinterpret_cast<float4*>(xs)[i] = v;
+    }
+    __syncthreads();
+    if (p.normw != nullptr) {
+      // RMSNorm prologue (K == KC): HF LlamaRMSNorm  w * (x * rsqrt(mean(x^2) + eps))
+      for (int b = warp; b < BT; b += GEMV_WARPS) {
+        float ss = 0.f;
+        for (int k = lane; k < KC; k += 32) { float v = xs[b * KC + k]; ss = fmaf(v, v, ss); }
+        ss = warp_sum(ss);
+        if (lane == 0) rinv[b] = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(__fdiv_rn(ss, (float)KC), p.eps)));
+      }
+      __syncthreads();
+      for (int i = tid; i < BT * KC; i += GEMV_WARPS * 32) {
+        const int b = i / KC, k = i % KC;
+        xs[i] = __fmul_rn(p.normw[k], __fmul_rn(xs[i], rinv[b]));
+      }
+      __syncthreads();
+      if (EPI == EPI_HEADS && p.hidden_out != nullptr && blockIdx.x == 0) {
+        // last_hidden_state of this step (gpt.py:430-436), written once
+        const int step = p.st->n_gen;
+        for (int i = tid; i < nb * KC; i += GEMV_WARPS * 32) {
+          const int b = i / KC, k = i % KC;
+          p.hidden_out[(size_t)(bbase + b) * p.hidden_stride + (size_t)step * KC + k] = xs[i];
+        }
+      }
+    }
+    if (has_task) {
+      float4 n0[6], n1[6];
+      const bool more = (c + 1) < nchunks;
+      if (more) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          n0[i] = ldg_stream(w0p + (c + 1) * (KC / 4) + i * 32);
+          n1[i] = ldg_stream(w1p + (c + 1) * (KC / 4) + i * 32);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+#pragma unroll
+        for (int b = 0; b < BT; ++b) {
+          const float4 xv = reinterpret_cast<const float4*>(xs)[b * (KC / 4) + i * 32 + lane];
+          acc0[b] = fmaf(w0[i].x, xv.x, acc0[b]); acc0[b] = fmaf(w0[i].y, xv.y, acc0[b]);
+          acc0[b] = fmaf(w0[i].z, xv.z, acc0[b]); acc0[b] = fmaf(w0[i].w, xv.w, acc0[b]);
+          acc1[b] = fmaf(w1[i].x, xv.x, acc1[b]); acc1[b] = fmaf(w1[i].y, xv.y, acc1[b]);
+          acc1[b] = fmaf(w1[i].z, xv.z, acc1[b]); acc1[b] = fmaf(w1[i].w, xv.w, acc1[b]);
+        }
+      }
+      if (more) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { w0[i] = n0[i]; w1[i] = n1[i]; }
+      }
+    }
+  }
+  if (!has_task) return;
+
+  warp_reduce_scatter<BT>(acc0);
+  warp_reduce_scatter<BT>(acc1);
+  constexpr int LPB = 32 / BT;  // lanes per batch row after the scatter
+  if ((lane % LPB) != 0 || (lane / LPB) >= nb) return;
+  const int b = bbase + lane / LPB;
+  const float v0 = acc0[0], v1 = acc1[0];
+
+  if (EPI == EPI_QKV) {
+    if (!p.active[b]) return;
+    const int half = p.hd / 2;
+    const int nq = p.Hq * half, nk = p.Hkv * half;
+    int t = task, which = 0;
+    if (t >= nq + nk) { which = 2; t -= nq + nk; }
+    else if (t >= nq) { which = 1; t -= nq; }
+    const int h = t / half, j = t % half;
+    const int pos = p.pos[b];
+    float o0 = v0, o1 = v1;
+    if (which < 2) {
+      // HF apply_rotary_pos_emb: q*cos + rotate_half(q)*sin, each product rounded separately
+      const float c0 = p.rope_cos[(size_t)pos * p.hd + j], s0 = p.rope_sin[(size_t)pos * p.hd + j];
+      const float c1 = p.rope_cos[(size_t)pos * p.hd + j + half], s1 = p.rope_sin[(size_t)pos * p.hd + j + half];
+      o0 = __fadd_rn(__fmul_rn(v0, c0), __fmul_rn(-v1, s0));
+      o1 = __fadd_rn(__fmul_rn(v1, c1), __fmul_rn(v0, s1));
+    }
+    if (which == 0) {
+      p.out[(size_t)b * p.Hq * p.hd + h * p.hd + j] = o0;
+      p.out[(size_t)b * p.Hq * p.hd + h * p.hd + j + half] = o1;
+    } else {
+      const int page = p.block_table[b * p.pages_per_row + pos / kPageTokens];
+      float* dst = p.kv + kv_off(page, which - 1, h, pos % kPageTokens, p.Hkv, p.hd);
+      dst[j] = o0; dst[j + half] = o1;
+    }
+  } else if (EPI == EPI_OPROJ || EPI == EPI_DOWN) {
+    const int d = p.nrows;
+    p.xres[(size_t)b * d + r0] = __fadd_rn(p.xres[(size_t)b * d + r0], v0);
+    if (r1_valid) p.xres[(size_t)b * d + r1] = __fadd_rn(p.xres[(size_t)b * d + r1], v1);
+  } else if (EPI == EPI_GATEUP) {
+    // LlamaMLP: silu(gate) * up ; silu(x) = x / (1 + exp(-x))
+    const float sg = __fdiv_rn(v0, __fadd_rn(1.0f, expf(-v0)));
+    p.out[(size_t)b * p.I + task] = __fmul_rn(sg, v1);
+  } else {  // EPI_HEADS: logits rows ordered (b, q) like gpt.py:459-464
+    const int q0 = r0 / p.V, c0 = r0 % p.V;
+    p.out[((size_t)b * p.rows_per_item + q0) * p.V + c0] = v0;
+    if (r1_valid) {
+      const int q1 = r1 / p.V, c1 = r1 % p.V;
+      p.out[((size_t)b * p.rows_per_item + q1) * p.V + c1] = v1;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ step input
+struct InputP {
+  LoopState* st;
+  int decode;             // 0: prefill column, 1: decode step
+  int B, d, col, T0;
+  const float* emb;       // [B, T0, d] prompt embeddings
+  const uint8_t* mask;    // [B, T0]
+  const float* emb_code;  // [num_vq*num_audio, d]
+  const float* emb_text;  // [num_text, d]
+  const int32_t* ids_out; // [B, max_new, num_vq]
+  int max_new, num_vq, num_audio, infer_text;
+  float* x;               // [Bpad, d]
+  int* seq_len;           // [Bpad]
+  int* pos;               // [Bpad]
+  uint8_t* active;        // [Bpad]
+};
+
+#ifdef CTB_GPT_KERNELS_IMPL
+__global__ void k_input(const InputP p) {
+  const int b = blockIdx.x;
+  if (p.decode && p.st->all_finished) return;
+  float* x = p.x + (size_t)b * p.d;
+  bool act;
+  if (!p.decode) {
+    act = p.mask[(size_t)b * p.T0 + p.col] != 0;
+    const float* e = p.emb + ((size_t)b * p.T0 + p.col) * p.d;
+    for (int k = threadIdx.x; k < p.d; k += blockDim.x) x[k] = act ? e[k] : 0.f;
+  } else {
+    act = true;
+    const int32_t* id = p.ids_out + ((size_t)b * p.max_new + (p.st->n_gen - 1)) * p.num_vq;
+    if (p.infer_text) {
+      const float* e = p.emb_text + (size_t)id[0] * p.d;
+      for (int k = threadIdx.x; k < p.d; k += blockDim.x) x[k] = e[k];
+    } else {
+      // gpt.py:409-413: stack(code_emb, 3).sum(3)
+      for (int k = threadIdx.x; k < p.d; k += blockDim.x) {
+        float s = 0.f;
+        for (int q = 0; q < p.num_vq; ++q) s += p.emb_code[((size_t)q * p.num_audio + id[q]) * p.d + k];
+        x[k] = s;
+      }
+    }
+  }
+  if (threadIdx.x == 0) {
+    const int n = p.seq_len[b];
+    p.pos[b] = n;               // position id = #valid tokens before this one (gpt.py:234-241)
+    p.active[b] = act ? 1 : 0;
+    if (act) p.seq_len[b] = n + 1;
+  }
+}
+
+#endif  // CTB_GPT_KERNELS_IMPL
+
+// ------------------------------------------------------------------ decode attention
+struct AttnP {
+  const LoopState* st; int check_finished;
+  const float* q;        // [Bpad, Hq*hd]
+  const float* kv;       // this layer's pool
+  const int* block_table; int pages_per_row;
+  const int* pos; const uint8_t* active;
+  float* out;            // [Bpad, Hq*hd]
+  float* part;           // [B, Hq, nsplit_max, hd + 2]
+  int* counter;          // [B, Hq]
+  int Hq, Hkv, hd, nsplit_max;
+  float scaling;
+};
+
+// grid (nsplit_max, Hq, B); block ATT_THREADS.  hd == 64 assumed (checked on the host).
+#ifdef CTB_GPT_KERNELS_IMPL
+__global__ void __launch_bounds__(ATT_THREADS) k_attn(const AttnP p) {
+  if (p.check_finished && p.st->all_finished) return;
+  const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int HD = 64;
+  float* outp = p.out + (size_t)b * p.Hq * HD + h * HD;
+  if (!p.active[b]) { if (split == 0 && tid < HD) outp[tid] = 0.f; return; }
+  const int n = p.pos[b] + 1;  // keys 0..pos
+  const int nsplit = (n + ATT_CHUNK - 1) / ATT_CHUNK;
+  if (split >= nsplit) return;
+  const int t0 = split * ATT_CHUNK, t1 = min(n, t0 + ATT_CHUNK);
+  const int hk = h / (p.Hq / p.Hkv);
+  const int* bt = p.block_table + b * p.pages_per_row;
+
+  __shared__ float s_p[ATT_CHUNK];
+  __shared__ float s_red[ATT_THREADS / 32];
+  __shared__ float s_o[ATT_THREADS / 16][HD];
+  __shared__ int s_last;
+
+  // ---- scores: 8 lanes per key row (two float4 each), 4 keys per warp instruction
+  const int sub = lane & 7;
+  const float4 q0 = *reinterpret_cast<const float4*>(p.q + (size_t)b * p.Hq * HD + h * HD + sub * 8);
+  const float4 q1 = *reinterpret_cast<const float4*>(p.q + (size_t)b * p.Hq * HD + h * HD + sub * 8 + 4);
+  for (int t = t0 + warp * 4 + (lane >> 3); t < t0 + ATT_CHUNK; t += (ATT_THREADS / 32) * 4) {
+    float s = 0.f;
+    if (t < t1) {
+      const float* kr = p.kv + kv_off(bt[t / kPageTokens], 0, hk, t % kPageTokens, p.Hkv, HD) + sub * 8;
+      const float4 k0 = ldg_stream(reinterpret_cast<const float4*>(kr));
+      const float4 k1 = ldg_stream(reinterpret_cast<const float4*>(kr + 4));
+      s = q0.x * k0.x + q0.y * k0.y + q0.z * k0.z + q0.w * k0.w + q1.x * k1.x + q1.y * k1.y + q1.z * k1.z + q1.w * k1.w;
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    if (sub == 0 && t < t1) s_p[t - t0] = s * p.scaling;
+  }
+  __syncthreads();
+  // ---- chunk max / exp / sum
+  float m = -INFINITY;
+  for (int i = tid; i < t1 - t0; i += ATT_THREADS) m = fmaxf(m, s_p[i]);
+  m = warp_max(m);
+  if (lane == 0) s_red[warp] = m;
+  __syncthreads();
+  m = fmaxf(fmaxf(s_red[0], s_red[1]), fmaxf(s_red[2], s_red[3]));
+  __syncthreads();
+  float l = 0.f;
+  for (int i = tid; i < t1 - t0; i += ATT_THREADS) { const float e = expf(s_p[i] - m); s_p[i] = e; l += e; }
+  l = warp_sum(l);
+  if (lane == 0) s_red[warp] = l;
+  __syncthreads();
+  l = (s_red[0] + s_red[1]) + (s_red[2] + s_red[3]);
+  // ---- P.V : thread (tg, d4): tokens tg, tg+8, ... ; dims 4*d4..4*d4+3
+  const int tg = tid >> 4, d4 = tid & 15;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int t = t0 + tg; t < t1; t += ATT_THREADS / 16) {
+    const float* vr = p.kv + kv_off(bt[t / kPageTokens], 1, hk, t % kPageTokens, p.Hkv, HD) + d4 * 4;
+    const float4 v = ldg_stream(reinterpret_cast<const float4*>(vr));
+    const float w = s_p[t - t0];
+    acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y); acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+  }
+  *reinterpret_cast<float4*>(&s_o[tg][d4 * 4]) = acc;
+  __syncthreads();
+  float o = 0.f;
+  if (tid < HD) {
+#pragma unroll
+    for (int g = 0; g < ATT_THREADS / 16; ++g) o += s_o[g][tid];
+  }
+  if (nsplit == 1) {
+    if (tid < HD) outp[tid] = o / l;
+    return;
+  }
+  // ---- flash-decoding combine: the last CTA of this (b, h) merges the partials
+  float* part = p.part + (((size_t)b * p.Hq + h) * p.nsplit_max + split) * (HD + 2);
+  if (tid < HD) part[tid] = o;
+  if (tid == 0) { part[HD] = m; part[HD + 1] = l; }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(&p.counter[b * p.Hq + h], 1) == nsplit - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const float* pb = p.part + (((size_t)b * p.Hq + h) * p.nsplit_max) * (HD + 2);
+  float M = -INFINITY;
+  for (int s = 0; s < nsplit; ++s) M = fmaxf(M, __ldcg(pb + s * (HD + 2) + HD));
+  float L = 0.f, O = 0.f;
+  for (int s = 0; s < nsplit; ++s) {
+    const float w = expf(__ldcg(pb + s * (HD + 2) + HD) - M);
+    L = fmaf(w, __ldcg(pb + s * (HD + 2) + HD + 1), L);
+    if (tid < HD) O = fmaf(w, __ldcg(pb + s * (HD + 2) + tid), O);
+  }
+  if (tid < HD) outp[tid] = O / L;
+  if (tid == 0) p.counter[b * p.Hq + h] = 0;
+}
+
+#endif  // CTB_GPT_KERNELS_IMPL
+
+// ------------------------------------------------------------------ sampler
+struct SampleP {
+  const LoopState* st; int check_finished;
+  const float* logits;   // [rows, V]
+  int rows, V, rows_per_item;
+  ctb_sampler_config cfg;
+  const float* q_noise;  // [rows, V] or nullptr
+  const int32_t* gen_ids; // [rows/rpi, gen_stride, gen_inner]
+  int gen_stride, gen_inner;
+  int n_gen_fixed, step_fixed;  // used when st == nullptr (stand-alone ctb_sample)
+  int32_t* out_idx;      // [rows]
+};
+
+constexpr int SAMPLE_THREADS = 1024;
+__global__ void k_sample(const SampleP p);
+
+struct FinalP {
+  LoopState* st;
+  int B, rows_per_item, num_vq, max_new, eos;
+  const int32_t* idx;    // [B*rpi]
+  int32_t* ids_out;      // [B, max_new, num_vq]
+  uint8_t* finish; int32_t* end_idx;
+};
+__global__ void k_finalize(const FinalP p);
+
+}  // namespace ctb
