@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) k_sample(const SampleP p) {
         // always keep the min_keep largest: largest t with count(key >= t) >= min_keep
         uint32_t lo2 = 0u, hi2 = 0xffffffffu;
         while (lo2 < hi2) {
-          const uint32_t mid = lo2 + ((hi2 - lo2 + 1) >> 1);
+          const uint32_t mid = lo2 + (uint32_t)(((uint64_t)hi2 - lo2 + 1) >> 1);
           int cnt = 0;
           for (int v = tid; v < V; v += SAMPLE_THREADS) cnt += (float_key(s_x[v]) >= mid);
           cnt = block_sum_i(cnt, s_redi);
@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) k_sample(const SampleP p) {
       if (kk > 0) {
         uint32_t lo2 = 0u, hi2 = 0xffffffffu;
         while (lo2 < hi2) {
-          const uint32_t mid = lo2 + ((hi2 - lo2 + 1) >> 1);
+          const uint32_t mid = lo2 + (uint32_t)(((uint64_t)hi2 - lo2 + 1) >> 1);
           int cnt = 0;
           for (int v = tid; v < V; v += SAMPLE_THREADS) cnt += (float_key(s_x[v]) >= mid);
           cnt = block_sum_i(cnt, s_redi);
@@ -200,7 +200,15 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) k_sample(const SampleP p) {
       thr_key = max(t_p, t_k);
     }
   }
-  if (c.greedy) thr_key = float_key(mx);
+  if (c.greedy) {
+    // bench config C2: keep only the row arg-max; greedy == 2 takes it over the non-EOS tokens so
+    // that the EOS ban below can never empty the row
+    float gm = -INFINITY;
+    for (int v = tid; v < V; v += SAMPLE_THREADS)
+      if (!(c.greedy == 2 && v == c.eos_token)) gm = fmaxf(gm, s_x[v]);
+    gm = block_max_f(gm, s_redf);
+    thr_key = float_key(gm);
+  }
   if (tid == 0) s_thr = thr_key;
   __syncthreads();
   thr_key = s_thr;
@@ -210,7 +218,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) k_sample(const SampleP p) {
   float mx2 = -INFINITY;
   for (int v = tid; v < V; v += SAMPLE_THREADS) {
     float x = s_x[v];
-    if (float_key(x) < thr_key || (ban && v == c.eos_token)) x = -INFINITY;
+    if (float_key(x) < thr_key || ((ban || c.greedy == 2) && v == c.eos_token)) x = -INFINITY;
     s_x[v] = x;
     mx2 = fmaxf(mx2, x);
   }
@@ -243,7 +251,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) k_sample(const SampleP p) {
   if (tid == 0) {
     for (int w = 1; w < SAMPLE_THREADS / 32; ++w)
       if (s_bv[w] > best || (s_bv[w] == best && s_bi[w] < besti)) { best = s_bv[w]; besti = s_bi[w]; }
-    p.out_idx[row] = besti;
+    p.out_idx[row] = besti < V ? besti : 0;  // all-NaN row: ATen argmax returns the first index
   }
 }
 

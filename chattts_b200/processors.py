@@ -55,9 +55,12 @@ class TopKLogitsWarper:
 
 @dataclass
 class ArgmaxOnly:
-    """Extra processor for the 'greedy' benchmark config: keep the row max."""
+    """Extra processor for the 'greedy' benchmark config: keep the row max.
+    ``exclude_eos``: remove the EOS column first, so a forced-length run never ends up with an
+    empty row when the arg-max is EOS and ``min_new_token`` bans it afterwards."""
 
     greedy: bool = True
+    exclude_eos: bool = False
 
 
 def gen_logits(num_code: int, top_P=0.7, top_K=20, repetition_penalty=1.0) -> Tuple[list, list]:
@@ -108,7 +111,7 @@ def build_sampler_config(logits_processors: Sequence[object], temperature: Seque
             cfg.top_k = int(proc.top_k)  # HF already folded max(top_k, min_tokens_to_keep)
         elif getattr(proc, "greedy", False):
             kind = 4
-            cfg.greedy = 1
+            cfg.greedy = 2 if getattr(proc, "exclude_eos", False) else 1
         else:
             raise TypeError(
                 f"unsupported logits processor {type(proc).__name__}: the B200 sampler implements the reference's "

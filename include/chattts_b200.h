@@ -90,7 +90,8 @@ typedef struct ctb_sampler_config {
                                with the same torch.pow call as processors.py:28 */
   int32_t past_window;      /* 16 */
   int32_t penalty_max_ids;  /* rows >= this get no penalty (processors.py:24-27 quirk) */
-  int32_t greedy;           /* 1: keep only the row arg-max before softmax (bench config C2) */
+  int32_t greedy;           /* 1: keep only the row arg-max before softmax (bench config C2);
+                               2: arg-max over the non-EOS tokens (EOS removed as well) */
   int32_t eos_token;
   int32_t min_new_token;
   uint64_t philox_seed;     /* used only when q_noise == NULL (manual_seed=None path) */

@@ -80,6 +80,7 @@ class SamplerParams:
     penalty_window: int = 16
     min_keep: int = 3
     greedy: bool = False  # bench config C2: extra arg-max mask processor
+    greedy_exclude_eos: bool = False
 
 
 def sample_step(
@@ -103,6 +104,9 @@ def sample_step(
     if sp.top_k is not None:
         logits = top_k_filter(logits, sp.top_k, sp.min_keep)
     if sp.greedy:
+        if sp.greedy_exclude_eos:
+            logits = logits.clone()
+            logits[:, eos] = -float("inf")
         logits = logits.masked_fill(logits < logits.max(dim=-1, keepdim=True)[0], -float("inf"))
     if ban_eos:
         logits = logits.clone()

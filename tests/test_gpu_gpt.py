@@ -77,9 +77,9 @@ def test_greedy_processor_and_larger_weights():
     orc = GPTOracle(gs, es)
     ids, mask, tmask = synth_prompt_batch([9, 14], seed=4)
     ref = orc.generate(orc.embed_prompt(ids, tmask), ids, torch.tensor([0.3] * 4), 625, attention_mask=mask,
-                       max_new_token=20, min_new_token=20, sampler=SamplerParams(greedy=True), return_hidden=True,
+                       max_new_token=20, min_new_token=20, sampler=SamplerParams(greedy=True, greedy_exclude_eos=True), return_hidden=True,
                        manual_seed=1)
-    out = _run(gpt, embed, [9, 14], 4, 1, 20, extra=(ArgmaxOnly(),))[-1]
+    out = _run(gpt, embed, [9, 14], 4, 1, 20, extra=(ArgmaxOnly(exclude_eos=True),))[-1]
     for b in range(2):
         assert torch.equal(out.ids[b].cpu(), ref.ids[b])
         assert (out.hiddens[b].cpu() - ref.hiddens[b]).abs().max() < 2e-4
