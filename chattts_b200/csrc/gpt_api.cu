@@ -50,6 +50,7 @@ struct ctb_gpt {
   int32_t* ids_out;
   float* hiddens_out;
   cudaGraphExec_t graph_exec;
+  cudaStream_t cap_stream;
   bool use_graph;
 };
 
@@ -145,6 +146,7 @@ extern "C" int ctb_gpt_create(const ctb_gpt_config* c, const float* weights_dev,
 extern "C" int ctb_gpt_destroy(ctb_gpt* h) {
   if (!h) return CTB_OK;
   if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+  if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   void* ptrs[] = {h->x, h->qbuf, h->attn, h->mlp, h->logits, h->kv, h->part, h->block_table, h->seq_len,
                   h->pos, h->counter, h->end_idx, h->idx, h->active, h->finish, h->st};
   for (void* p : ptrs) if (p) cudaFree(p);
@@ -191,88 +193,141 @@ static int launch_sample(const SampleP& sp, cudaStream_t s) {
   return CTB_OK;
 }
 
+struct StepCtx {
+  GemvP g;
+  AttnP a;
+  int bt, ntiles, decode;
+};
+
+static StepCtx make_ctx(ctb_gpt* h, int decode) {
+  const ctb_gpt_config& c = h->cfg;
+  const ctb_gpt_layout& L = h->lay;
+  StepCtx x{};
+  x.decode = decode;
+  x.bt = bt_for(h->B);
+  x.ntiles = (h->B + x.bt - 1) / x.bt;
+  GemvP& g = x.g;
+  g.B = h->B; g.st = h->st; g.check_finished = decode; g.eps = c.rms_eps;
+  g.block_table = h->block_table; g.pages_per_row = h->pages_per_row; g.pos = h->pos; g.active = h->active;
+  g.rope_cos = h->W + L.rope_cos; g.rope_sin = h->W + L.rope_sin;
+  g.Hq = c.num_heads; g.Hkv = c.num_kv_heads; g.hd = c.head_dim; g.I = c.intermediate_size; g.xres = h->x;
+  AttnP& a = x.a;
+  a.st = h->st; a.check_finished = decode; a.q = h->qbuf; a.block_table = h->block_table;
+  a.pages_per_row = h->pages_per_row; a.pos = h->pos; a.active = h->active; a.out = h->attn; a.part = h->part;
+  a.counter = h->counter; a.Hq = c.num_heads; a.Hkv = c.num_kv_heads; a.hd = c.head_dim;
+  a.nsplit_max = h->nsplit_max; a.scaling = 1.0f / sqrtf((float)c.head_dim);
+  return x;
+}
+
+// kind: 0 qkv(+rope+kv append), 1 attention, 2 o-proj(+residual), 3 gate/up(+silu*mul), 4 down(+residual)
+static int launch_layer_kernel(ctb_gpt* h, const StepCtx& x, int l, int kind, cudaStream_t s) {
+  const ctb_gpt_config& c = h->cfg;
+  const ctb_gpt_layout& L = h->lay;
+  const int d = c.hidden_size, I = c.intermediate_size, hd = c.head_dim;
+  const float* Wl = h->W + L.layer0 + (int64_t)l * L.layer_stride;
+  float* kvl = h->kv + (size_t)l * h->kv_layer_floats;
+  GemvP p = x.g;
+  switch (kind) {
+    case 0:
+      p.W = Wl + L.wqkv; p.K = d; p.nrows = (c.num_heads + 2 * c.num_kv_heads) * hd; p.ntasks = p.nrows / 2;
+      p.xin = h->x; p.normw = Wl + L.ln1; p.out = h->qbuf; p.kv = kvl;
+      return launch_gemv<EPI_QKV>(x.bt, p, x.ntiles, s);
+    case 1: {
+      AttnP a = x.a;
+      a.kv = kvl;
+      // context after this call <= T0 + max_new: only launch splits that can be populated
+      const int max_ctx = std::min(c.max_context, h->T0 + h->max_new);
+      dim3 agrid((max_ctx + ATT_CHUNK - 1) / ATT_CHUNK, c.num_heads, h->B);
+      k_attn<<<agrid, ATT_THREADS, 0, s>>>(a);
+      CTB_LAUNCH_CHECK();
+      return CTB_OK;
+    }
+    case 2:
+      p.W = Wl + L.wo; p.K = c.num_heads * hd; p.nrows = d; p.ntasks = d / 2; p.xin = h->attn; p.normw = nullptr;
+      return launch_gemv<EPI_OPROJ>(x.bt, p, x.ntiles, s);
+    case 3:
+      p.W = Wl + L.wgate_up; p.K = d; p.nrows = 2 * I; p.ntasks = I; p.xin = h->x; p.normw = Wl + L.ln2;
+      p.out = h->mlp;
+      return launch_gemv<EPI_GATEUP>(x.bt, p, x.ntiles, s);
+    case 4:
+      p.W = Wl + L.wdown; p.K = I; p.nrows = d; p.ntasks = d / 2; p.xin = h->mlp; p.normw = nullptr;
+      return launch_gemv<EPI_DOWN>(x.bt, p, x.ntiles, s);
+  }
+  return set_err(CTB_ERR_ARG, "bad kernel kind %d", kind);
+}
+
+static int launch_heads(ctb_gpt* h, const StepCtx& x, cudaStream_t s) {
+  const ctb_gpt_config& c = h->cfg;
+  const int rpi = h->infer_text ? 1 : c.num_vq;
+  const int V = h->infer_text ? c.num_text_tokens : c.num_audio_tokens;
+  GemvP hp = x.g;
+  hp.W = h->W + (h->infer_text ? h->lay.head_text : h->lay.head_code);
+  hp.K = c.hidden_size; hp.nrows = rpi * V; hp.ntasks = (hp.nrows + 1) / 2; hp.xin = h->x;
+  hp.normw = h->W + h->lay.final_norm; hp.out = h->logits; hp.rows_per_item = rpi; hp.V = V;
+  hp.hidden_out = h->hiddens_out; hp.hidden_stride = h->max_new * c.hidden_size;
+  return launch_gemv<EPI_HEADS>(x.bt, hp, x.ntiles, s);
+}
+
+static int launch_sampler(ctb_gpt* h, const StepCtx& x, cudaStream_t s) {
+  const ctb_gpt_config& c = h->cfg;
+  const int rpi = h->infer_text ? 1 : c.num_vq;
+  SampleP sp{};
+  sp.st = h->st; sp.check_finished = x.decode; sp.logits = h->logits; sp.rows = h->B * rpi;
+  sp.V = h->infer_text ? c.num_text_tokens : c.num_audio_tokens;
+  sp.rows_per_item = rpi; sp.cfg = h->sampler; sp.q_noise = h->q_noise; sp.gen_ids = h->ids_out;
+  sp.gen_stride = h->max_new; sp.gen_inner = c.num_vq; sp.out_idx = h->idx;
+  return launch_sample(sp, s);
+}
+
 // One loop iteration.  col >= 0: prefill column `col` of the prompt; col < 0: decode step.
 // sample: run heads + sampler + finalize (last prompt column and every decode step).
 static int enqueue_step(ctb_gpt* h, int col, bool sample, cudaStream_t s) {
   const ctb_gpt_config& c = h->cfg;
   const ctb_gpt_layout& L = h->lay;
-  const int B = h->B, bt = bt_for(B), ntiles = (B + bt - 1) / bt;
   const int decode = col < 0;
-  const int d = c.hidden_size, I = c.intermediate_size, hd = c.head_dim;
   int rc;
 
   InputP ip{};
-  ip.st = h->st; ip.decode = decode; ip.B = B; ip.d = d; ip.col = decode ? 0 : col; ip.T0 = h->T0;
+  ip.st = h->st; ip.decode = decode; ip.B = h->B; ip.d = c.hidden_size; ip.col = decode ? 0 : col; ip.T0 = h->T0;
   ip.emb = h->emb; ip.mask = h->mask;
   ip.emb_code = h->W + L.emb_code; ip.emb_text = h->W + L.emb_text;
   ip.ids_out = h->ids_out; ip.max_new = h->max_new; ip.num_vq = c.num_vq; ip.num_audio = c.num_audio_tokens;
   ip.infer_text = h->infer_text;
   ip.x = h->x; ip.seq_len = h->seq_len; ip.pos = h->pos; ip.active = h->active;
-  k_input<<<B, 256, 0, s>>>(ip);
+  k_input<<<h->B, 256, 0, s>>>(ip);
   CTB_LAUNCH_CHECK();
 
-  GemvP g{};
-  g.B = B; g.st = h->st; g.check_finished = decode; g.eps = c.rms_eps;
-  g.block_table = h->block_table; g.pages_per_row = h->pages_per_row; g.pos = h->pos; g.active = h->active;
-  g.rope_cos = h->W + L.rope_cos; g.rope_sin = h->W + L.rope_sin;
-  g.Hq = c.num_heads; g.Hkv = c.num_kv_heads; g.hd = hd; g.I = I; g.xres = h->x;
-
-  AttnP a{};
-  a.st = h->st; a.check_finished = decode; a.q = h->qbuf; a.block_table = h->block_table;
-  a.pages_per_row = h->pages_per_row; a.pos = h->pos; a.active = h->active; a.out = h->attn; a.part = h->part;
-  a.counter = h->counter; a.Hq = c.num_heads; a.Hkv = c.num_kv_heads; a.hd = hd; a.nsplit_max = h->nsplit_max;
-  a.scaling = 1.0f / sqrtf((float)hd);
-
-  for (int l = 0; l < c.num_layers; ++l) {
-    const float* Wl = h->W + L.layer0 + (int64_t)l * L.layer_stride;
-    float* kvl = h->kv + (size_t)l * h->kv_layer_floats;
-    GemvP q = g;
-    q.W = Wl + L.wqkv; q.K = d; q.nrows = (c.num_heads + 2 * c.num_kv_heads) * hd; q.ntasks = q.nrows / 2;
-    q.xin = h->x; q.normw = Wl + L.ln1; q.out = h->qbuf; q.kv = kvl;
-    if ((rc = launch_gemv<EPI_QKV>(bt, q, ntiles, s))) return rc;
-
-    a.kv = kvl;
-    // context after this step <= T0 + max_new; only launch the splits that can be populated
-    const int max_ctx = std::min(c.max_context, h->T0 + h->max_new);
-    dim3 agrid((max_ctx + ATT_CHUNK - 1) / ATT_CHUNK, c.num_heads, B);
-    k_attn<<<agrid, ATT_THREADS, 0, s>>>(a);
-    CTB_LAUNCH_CHECK();
-
-    GemvP o = g;
-    o.W = Wl + L.wo; o.K = c.num_heads * hd; o.nrows = d; o.ntasks = d / 2; o.xin = h->attn; o.normw = nullptr;
-    if ((rc = launch_gemv<EPI_OPROJ>(bt, o, ntiles, s))) return rc;
-
-    GemvP gu = g;
-    gu.W = Wl + L.wgate_up; gu.K = d; gu.nrows = 2 * I; gu.ntasks = I; gu.xin = h->x; gu.normw = Wl + L.ln2;
-    gu.out = h->mlp;
-    if ((rc = launch_gemv<EPI_GATEUP>(bt, gu, ntiles, s))) return rc;
-
-    GemvP dn = g;
-    dn.W = Wl + L.wdown; dn.K = I; dn.nrows = d; dn.ntasks = d / 2; dn.xin = h->mlp; dn.normw = nullptr;
-    if ((rc = launch_gemv<EPI_DOWN>(bt, dn, ntiles, s))) return rc;
-  }
+  const StepCtx x = make_ctx(h, decode);
+  for (int l = 0; l < c.num_layers; ++l)
+    for (int kind = 0; kind < 5; ++kind)
+      if ((rc = launch_layer_kernel(h, x, l, kind, s))) return rc;
   if (!sample) return CTB_OK;
-
-  const int rpi = h->infer_text ? 1 : c.num_vq;
-  const int V = h->infer_text ? c.num_text_tokens : c.num_audio_tokens;
-  GemvP hp = g;
-  hp.W = h->W + (h->infer_text ? L.head_text : L.head_code);
-  hp.K = d; hp.nrows = rpi * V; hp.ntasks = (hp.nrows + 1) / 2; hp.xin = h->x; hp.normw = h->W + L.final_norm;
-  hp.out = h->logits; hp.rows_per_item = rpi; hp.V = V;
-  hp.hidden_out = h->hiddens_out; hp.hidden_stride = h->max_new * d;
-  if ((rc = launch_gemv<EPI_HEADS>(bt, hp, ntiles, s))) return rc;
-
-  SampleP sp{};
-  sp.st = h->st; sp.check_finished = decode; sp.logits = h->logits; sp.rows = B * rpi; sp.V = V;
-  sp.rows_per_item = rpi; sp.cfg = h->sampler; sp.q_noise = h->q_noise; sp.gen_ids = h->ids_out;
-  sp.gen_stride = h->max_new; sp.gen_inner = c.num_vq; sp.out_idx = h->idx;
-  if ((rc = launch_sample(sp, s))) return rc;
+  if ((rc = launch_heads(h, x, s))) return rc;
+  if ((rc = launch_sampler(h, x, s))) return rc;
 
   FinalP fp{};
-  fp.st = h->st; fp.B = B; fp.rows_per_item = rpi; fp.num_vq = c.num_vq; fp.max_new = h->max_new;
-  fp.eos = h->sampler.eos_token; fp.idx = h->idx; fp.ids_out = h->ids_out; fp.finish = h->finish; fp.end_idx = h->end_idx;
+  fp.st = h->st; fp.B = h->B; fp.rows_per_item = h->infer_text ? 1 : c.num_vq; fp.num_vq = c.num_vq;
+  fp.max_new = h->max_new; fp.eos = h->sampler.eos_token; fp.idx = h->idx; fp.ids_out = h->ids_out;
+  fp.finish = h->finish; fp.end_idx = h->end_idx;
   k_finalize<<<1, 256, 0, s>>>(fp);
   CTB_LAUNCH_CHECK();
+  return CTB_OK;
+}
+
+// Measurement hook (bench.py roofline): launch ONE kernel kind for every layer (20 launches over
+// 20 different weight slabs, so nothing is L2-resident between launches) on the state left by the
+// last generate call.  kind 0..4 as above, 5 = heads, 6 = sampler.  Results of a later decode are
+// undefined after this call (the residual stream is overwritten); call ctb_gpt_begin again.
+extern "C" int ctb_gpt_profile_kernel(ctb_gpt* h, int32_t kind, void* stream) {
+  if (!h || !h->started) return set_err(CTB_ERR_STATE, "ctb_gpt_begin has not been called");
+  cudaStream_t s = (cudaStream_t)stream;
+  StepCtx x = make_ctx(h, 0);
+  x.g.check_finished = 0; x.a.check_finished = 0;
+  int rc;
+  if (kind == 5) return launch_heads(h, x, s);
+  if (kind == 6) return launch_sampler(h, x, s);
+  for (int l = 0; l < h->cfg.num_layers; ++l)
+    if ((rc = launch_layer_kernel(h, x, l, kind, s))) return rc;
   return CTB_OK;
 }
 
@@ -308,10 +363,13 @@ extern "C" int ctb_gpt_decode(ctb_gpt* h, int32_t n_steps, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   int rc;
   if (h->use_graph && !h->graph_exec) {
+    // capture on a private stream (the caller's may be the legacy default stream, which cannot
+    // be captured); the instantiated graph is then launched on the caller's stream
     cudaGraph_t graph;
-    CTB_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-    rc = enqueue_step(h, -1, true, s);
-    cudaError_t e = cudaStreamEndCapture(s, &graph);
+    if (!h->cap_stream) CTB_CUDA(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+    CTB_CUDA(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
+    rc = enqueue_step(h, -1, true, h->cap_stream);
+    cudaError_t e = cudaStreamEndCapture(h->cap_stream, &graph);
     if (rc) return rc;
     if (e != cudaSuccess) return set_err(CTB_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
     CTB_CUDA(cudaGraphInstantiate(&h->graph_exec, graph, 0));

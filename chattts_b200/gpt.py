@@ -111,13 +111,7 @@ class GPT:
         chattts_b200/dist.py) - then ``gpt_state`` may be None."""
         _lib.require_cuda()
         lib = _lib.load()
-        c = self.config
-        cc = _lib.GptConfig(c.hidden_size, c.intermediate_size, c.num_hidden_layers, c.num_attention_heads,
-                            c.num_key_value_heads, c.head_dim, c.num_vq, c.num_audio_tokens, c.num_text_tokens,
-                            c.max_position_embeddings, c.rms_norm_eps, self.max_batch, self.max_context)
-        lay = _lib.GptLayout()
-        _lib.check(lib.ctb_gpt_layout_query(C.byref(cc), C.byref(lay)))
-        self._cc, self._layout = cc, lay
+        cc, lay = self.query_layout()
         if weights_blob is None:
             weights_blob = self.pack_weights(gpt_state, lay).to(self.device_gpt)
         assert weights_blob.numel() == lay.total and weights_blob.dtype == torch.float32
@@ -127,6 +121,18 @@ class GPT:
             self._handle = C.c_void_p()
         with torch.cuda.device(self.device_gpt):
             _lib.check(lib.ctb_gpt_create(C.byref(cc), C.c_void_p(self._weights.data_ptr()), C.byref(self._handle)))
+
+    def query_layout(self):
+        """(ctb_gpt_config, ctb_gpt_layout) for this model shape - the C side owns the blob layout."""
+        lib = _lib.load()
+        c = self.config
+        cc = _lib.GptConfig(c.hidden_size, c.intermediate_size, c.num_hidden_layers, c.num_attention_heads,
+                            c.num_key_value_heads, c.head_dim, c.num_vq, c.num_audio_tokens, c.num_text_tokens,
+                            c.max_position_embeddings, c.rms_norm_eps, self.max_batch, self.max_context)
+        lay = _lib.GptLayout()
+        _lib.check(lib.ctb_gpt_layout_query(C.byref(cc), C.byref(lay)))
+        self._cc, self._layout = cc, lay
+        return cc, lay
 
     def pack_weights(self, s: Dict[str, torch.Tensor], lay) -> torch.Tensor:
         c = self.config
@@ -182,6 +188,24 @@ class GPT:
         if isinstance(hiddens, torch.Tensor):
             hiddens = [hiddens[i].narrow(0, 0, int(n)) for i, n in enumerate(end_idx.int())]
         return self.GenerationOutputs(ids=ids, attentions=attentions, hiddens=hiddens)
+
+    # ------------------------------------------------------------------ device-resident entry
+    def enqueue_generate(self, emb_d: torch.Tensor, mask_d: torch.Tensor, cfg, q_d: Optional[torch.Tensor],
+                         max_new_token: int, infer_text: bool, ids_out: torch.Tensor,
+                         hid_out: Optional[torch.Tensor], n_steps: Optional[int] = None) -> None:
+        """Enqueue prefill + ``n_steps`` loop iterations on the current stream with every buffer
+        already resident on the device; never synchronises (bench.py times this with CUDA events)."""
+        lib = _lib.load()
+        B, T0 = int(emb_d.shape[0]), int(emb_d.shape[1])
+        stream_ptr = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _lib.check(lib.ctb_gpt_begin(
+            self._handle, B, T0, C.c_void_p(emb_d.data_ptr()), C.c_void_p(mask_d.data_ptr()), C.byref(cfg),
+            C.c_void_p(q_d.data_ptr()) if q_d is not None else None, max_new_token, int(bool(infer_text)),
+            C.c_void_p(ids_out.data_ptr()), C.c_void_p(hid_out.data_ptr()) if hid_out is not None else None,
+            stream_ptr))
+        n = max_new_token - 1 if n_steps is None else n_steps
+        if n > 0:
+            _lib.check(lib.ctb_gpt_decode(self._handle, n, stream_ptr))
 
     # ------------------------------------------------------------------ the loop
     @torch.no_grad()

@@ -133,6 +133,11 @@ typedef struct ctb_gpt_status {
 int ctb_gpt_status_query(ctb_gpt* h, ctb_gpt_status* out, int32_t* end_idx_host, uint8_t* finish_host,
                          void* stream);
 
+/* Measurement hook for bench.py's roofline: launches ONE kernel kind once per layer on the
+ * state left by the last generate call (kind 0 qkv, 1 attention, 2 o-proj, 3 gate/up, 4 down;
+ * 5 = heads, 6 = sampler: one launch).  No reference counterpart. */
+int ctb_gpt_profile_kernel(ctb_gpt* h, int32_t kind, void* stream);
+
 /* Stand-alone sampling tail over caller-provided logits (minimum slice of SURVEY.md 7.2;
  * same kernel the decode loop uses).
  *   logits_dev [rows, V] fp32 (not modified); gen_ids_dev [rows/rpi, gen_stride, rpi] int32 with
