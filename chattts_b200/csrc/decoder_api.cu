@@ -1,20 +1,270 @@
-// extern "C" entry points for hot path 2 (token -> waveform).  Kernels: decoder_kernels.cuh
-#include "common.cuh"
+// extern "C" entry points for hot path 2 (token -> waveform); see include/chattts_b200.h.
+#include "decoder_kernels.cuh"
 
 using namespace ctb;
 
-struct ctb_decoder { int dummy; };
+namespace {
 
-extern "C" int64_t ctb_dvae_blob_floats(const ctb_convstack_config*) { return 0; }
-extern "C" int64_t ctb_vocos_blob_floats(const ctb_vocos_config*) { return 0; }
-extern "C" int ctb_decoder_create(const ctb_convstack_config*, const float*, const ctb_vocos_config*, const float*,
-                                  int32_t, int32_t, ctb_decoder**) {
-  return set_err(CTB_ERR_STATE, "decoder path not built yet");
+struct BlockOff {  // one ConvNeXt block inside a blob (float offsets)
+  int64_t dw_w, dw_b, ln_w, ln_b, pw1_w, pw1_b, pw2_w, pw2_b, gamma;
+};
+
+struct DvaeOff {
+  int64_t in0_w, in0_b, in2_w, in2_b, conv_out_w, out_conv_w, coef, vq_w, vq_b, total;
+  BlockOff blk[64];
+};
+struct VocosOff {
+  int64_t embed_w, embed_b, norm_w, norm_b, fin_w, fin_b, head_w, head_b, basis, window, total;
+  BlockOff blk[64];
+};
+
+constexpr int MEL = 100, MEL_PAD = 128;
+
+int64_t take(int64_t& off, int64_t n) { const int64_t o = off; off += (n + 3) / 4 * 4; return o; }
+
+void block_layout(BlockOff& b, int64_t& off, int C, int inter) {
+  b.dw_w = take(off, 7LL * C); b.dw_b = take(off, C); b.ln_w = take(off, C); b.ln_b = take(off, C);
+  b.pw1_w = take(off, (int64_t)inter * C); b.pw1_b = take(off, inter);
+  b.pw2_w = take(off, (int64_t)C * inter); b.pw2_b = take(off, C); b.gamma = take(off, C);
 }
-extern "C" int ctb_decoder_destroy(ctb_decoder*) { return CTB_OK; }
-extern "C" int ctb_dvae_decode(ctb_decoder*, const void*, int32_t, int32_t, int32_t, float*, void*) {
-  return set_err(CTB_ERR_STATE, "decoder path not built yet");
+
+// Blob order (all fp32, every tensor padded to a multiple of 4 floats); the Python packer in
+// chattts_b200/decoder.py writes the same sequence and checks the total against these functions.
+DvaeOff dvae_layout(const ctb_convstack_config& c) {
+  DvaeOff o{};
+  int64_t off = 0;
+  o.in0_w = take(off, (int64_t)c.bn_dim * 3 * c.idim);       // [bn, 3*idim]  tap-major K
+  o.in0_b = take(off, c.bn_dim);
+  o.in2_w = take(off, (int64_t)c.hidden * 3 * c.bn_dim);     // [hidden, 3*bn]
+  o.in2_b = take(off, c.hidden);
+  for (int i = 0; i < c.n_layer; ++i) block_layout(o.blk[i], off, c.hidden, 4 * c.hidden);
+  o.conv_out_w = take(off, (int64_t)c.odim * c.hidden);      // [odim, hidden]
+  o.out_conv_w = take(off, (int64_t)MEL_PAD * 3 * c.out_dim); // [128 (100 + zero rows), 3*out_dim]
+  o.coef = take(off, MEL_PAD);
+  if (c.vq_dim > 0) {
+    const int per_group = c.vq_dim / c.vq_groups;
+    o.vq_w = take(off, (int64_t)c.vq_groups * per_group * 4); // [G][dim/G][4]
+    o.vq_b = take(off, (int64_t)c.vq_groups * per_group);
+  }
+  o.total = off;
+  return o;
 }
-extern "C" int ctb_vocos_decode(ctb_decoder*, const float*, int32_t, int32_t, float*, void*) {
-  return set_err(CTB_ERR_STATE, "decoder path not built yet");
+
+int spec_k(const ctb_vocos_config& c) { return ((c.n_fft + 2) + 15) / 16 * 16; }  // 1026 -> 1040
+
+VocosOff vocos_layout(const ctb_vocos_config& c) {
+  VocosOff o{};
+  int64_t off = 0;
+  o.embed_w = take(off, (int64_t)c.dim * 7 * MEL_PAD);       // [dim, 7*128] (mel channels padded)
+  o.embed_b = take(off, c.dim);
+  o.norm_w = take(off, c.dim); o.norm_b = take(off, c.dim);
+  for (int i = 0; i < c.num_layers; ++i) block_layout(o.blk[i], off, c.dim, c.intermediate_dim);
+  o.fin_w = take(off, c.dim); o.fin_b = take(off, c.dim);
+  o.head_w = take(off, (int64_t)spec_k(c) * c.dim);          // rows interleaved (mag_k, phase_k), zero pad rows
+  o.head_b = take(off, spec_k(c));
+  o.basis = take(off, (int64_t)c.n_fft * spec_k(c));         // [n_fft, spec_k] windowed inverse real DFT
+  o.window = take(off, c.n_fft);
+  o.total = off;
+  return o;
+}
+
+}  // namespace
+
+struct ctb_decoder {
+  ctb_convstack_config dc;
+  ctb_vocos_config vc;
+  DvaeOff dl;
+  VocosOff vl;
+  const float* dW;
+  const float* vW;
+  int max_batch, max_tokens;
+  size_t max_rows;  // max_batch * 2 * max_tokens frames
+  float *bufA, *bufB, *bufH, *mel_tm, *staged_in;
+};
+
+extern "C" int64_t ctb_dvae_blob_floats(const ctb_convstack_config* c) { return c ? dvae_layout(*c).total : -1; }
+extern "C" int64_t ctb_vocos_blob_floats(const ctb_vocos_config* c) { return c ? vocos_layout(*c).total : -1; }
+
+extern "C" int ctb_decoder_destroy(ctb_decoder* h) {
+  if (!h) return CTB_OK;
+  void* ptrs[] = {h->bufA, h->bufB, h->bufH, h->mel_tm, h->staged_in};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  delete h;
+  return CTB_OK;
+}
+
+extern "C" int ctb_decoder_create(const ctb_convstack_config* dc, const float* dvae_blob_dev,
+                                  const ctb_vocos_config* vc, const float* vocos_blob_dev, int32_t max_batch,
+                                  int32_t max_tokens, ctb_decoder** out) {
+  // either blob may be NULL: the handle then serves only the other half (DVAE-only / Vocos-only)
+  if (!dc || !vc || (!dvae_blob_dev && !vocos_blob_dev) || !out) return set_err(CTB_ERR_ARG, "null argument");
+  if (dc->kernel != 7 || dc->n_layer > 64 || vc->num_layers > 64) return set_err(CTB_ERR_ARG, "unsupported conv stack");
+  if (dc->idim % 16 || dc->bn_dim % 16 || dc->hidden % 128 || dc->hidden > 512 || dc->odim % 16 || dc->out_dim % 16)
+    return set_err(CTB_ERR_ARG, "dvae channel counts must be multiples of 16 (hidden: of 128, <= 512)");
+  if (vc->input_channels != MEL || vc->dim % 128 || vc->dim > 512 || vc->intermediate_dim % 16 || vc->n_fft % 16 ||
+      vc->hop_length * 4 != vc->n_fft)
+    return set_err(CTB_ERR_ARG, "unsupported vocos shape");
+  if (dc->vq_dim > 0 && (dc->vq_levels < 2 || dc->vq_dim % dc->vq_groups || dc->vq_dim / dc->vq_groups != dc->idim))
+    return set_err(CTB_ERR_ARG, "vq_dim / vq_groups must equal the stack's idim");
+  int ndev = 0;
+  CTB_CUDA(cudaGetDeviceCount(&ndev));
+  if (ndev < 1) return set_err(CTB_ERR_CUDA, "no CUDA device: chattts_b200 has no CPU path");
+  ctb_decoder* h = new ctb_decoder();
+  memset(h, 0, sizeof(*h));
+  h->dc = *dc; h->vc = *vc; h->dl = dvae_layout(*dc); h->vl = vocos_layout(*vc);
+  h->dW = dvae_blob_dev; h->vW = vocos_blob_dev;
+  h->max_batch = max_batch; h->max_tokens = max_tokens;
+  h->max_rows = (size_t)max_batch * 2 * max_tokens;
+  const size_t R = h->max_rows;
+  const size_t wide = std::max((size_t)std::max(4 * dc->hidden, vc->intermediate_dim), (size_t)vc->n_fft);
+  const size_t narrow = std::max((size_t)std::max(std::max(dc->hidden, dc->idim), vc->dim), (size_t)dc->odim);
+  cudaError_t e = cudaSuccess;
+  auto A = [&](float** p, size_t n) { if (e == cudaSuccess) e = cudaMalloc((void**)p, n * sizeof(float)); };
+  A(&h->bufA, R * std::max(narrow, (size_t)spec_k(*vc)));
+  A(&h->bufB, R * narrow);
+  A(&h->bufH, R * wide);
+  A(&h->mel_tm, R * MEL_PAD);
+  A(&h->staged_in, R * dc->idim);
+  if (e != cudaSuccess) {
+    ctb_decoder_destroy(h);
+    return set_err(CTB_ERR_NOMEM, "decoder buffers: %s", cudaGetErrorString(e));
+  }
+  *out = h;
+  return CTB_OK;
+}
+
+// ------------------------------------------------------------------ launch helpers
+template <int EPI>
+static int gemm(cudaStream_t s, const float* A, int lda, int M, int N, int K, int taps, int Cin, int dil, int pad,
+                int F, const float* W, const float* bias, const float* gamma, const float* res, int ldres, float* C,
+                int ldc) {
+  GemmP p{};
+  p.A = A; p.lda = lda; p.M = M; p.N = N; p.K = K; p.taps = taps; p.Cin = Cin; p.dil = dil; p.pad = pad; p.F = F;
+  p.W = W; p.bias = bias; p.gamma = gamma; p.res = res; p.ldres = ldres; p.C = C; p.ldc = ldc;
+  dim3 grid((N + GBN - 1) / GBN, (M + GBM - 1) / GBM);
+  k_sgemm_nt<EPI><<<grid, 256, 0, s>>>(p);
+  CTB_LAUNCH_CHECK();
+  return CTB_OK;
+}
+
+static int dwln(cudaStream_t s, const float* x, float* out, int M, int F, int C, int taps, int dil, const float* w,
+                const float* b, const float* lnw, const float* lnb) {
+  DwLnP p{x, out, M, F, C, taps, dil, w, b, lnw, lnb, 1e-6f};
+  const int blocks = (M + 7) / 8;
+  switch (C / 128) {
+    case 1: k_dwconv_ln<1><<<blocks, 256, 0, s>>>(p); break;
+    case 2: k_dwconv_ln<2><<<blocks, 256, 0, s>>>(p); break;
+    case 3: k_dwconv_ln<3><<<blocks, 256, 0, s>>>(p); break;
+    default: k_dwconv_ln<4><<<blocks, 256, 0, s>>>(p); break;
+  }
+  CTB_LAUNCH_CHECK();
+  return CTB_OK;
+}
+
+// x (time-major [M, C]) -> x through one ConvNeXt block; tmp = [M, C], hbuf = [M, inter]
+static int convnext(cudaStream_t s, const float* W, const BlockOff& b, float* x, float* tmp, float* hbuf, int M,
+                    int F, int C, int inter, int dil) {
+  int rc;
+  if ((rc = dwln(s, x, tmp, M, F, C, 7, dil, W + b.dw_w, W + b.dw_b, W + b.ln_w, W + b.ln_b))) return rc;
+  if ((rc = gemm<GE_GELU>(s, tmp, C, M, inter, C, 1, C, 1, 0, F, W + b.pw1_w, W + b.pw1_b, nullptr, nullptr, 0, hbuf,
+                          inter))) return rc;
+  return gemm<GE_SCALE_RES>(s, hbuf, inter, M, C, inter, 1, inter, 1, 0, F, W + b.pw2_w, W + b.pw2_b, W + b.gamma, x,
+                            C, x, C);
+}
+
+// in_layout: 0 = channels-first [B, C, T] fp32 (DVAE.__call__ layout), 1 = token-major [B, T, C] fp32
+// (the decode loop's hidden states; frame doubling is then a re-interpretation), 2 = codes [B, G*R, T] int32
+static int dvae_run(ctb_decoder* h, const void* in, int layout, int B, int T, float* mel_cf, cudaStream_t s) {
+  const ctb_convstack_config& c = h->dc;
+  const DvaeOff& L = h->dl;
+  const float* W = h->dW;
+  const int F = 2 * T, M = B * F;
+  int rc;
+  const float* x0;
+  if (layout == 1) {
+    x0 = static_cast<const float*>(in);
+  } else if (layout == 0) {
+    dim3 g((T + 31) / 32, (2 * c.idim + 31) / 32, B);
+    k_cf_to_tm_doubled<<<g, dim3(32, 8), 0, s>>>(static_cast<const float*>(in), h->staged_in, B, 2 * c.idim, T);
+    CTB_LAUNCH_CHECK();
+    x0 = h->staged_in;
+  } else {
+    if (c.vq_dim <= 0) return set_err(CTB_ERR_ARG, "this decoder has no VQ layer (use_decoder=True model)");
+    if (c.vq_groups != 2) return set_err(CTB_ERR_ARG, "vq_groups must be 2 (one group per doubled frame)");
+    GfsqP g{};
+    g.ids = static_cast<const int32_t*>(in); g.out = h->staged_in; g.B = B; g.T = T; g.G = c.vq_groups;
+    g.R = c.vq_residual; g.levels = c.vq_levels & 0xff; g.nlev = 4; g.per_group = c.vq_dim / c.vq_groups;
+    g.scale_base = (float)((c.vq_levels >> 8) ? (c.vq_levels >> 8) : (g.levels - 1));
+    g.w = W + L.vq_w; g.b = W + L.vq_b;
+    k_gfsq_dequant<<<B * T * c.vq_groups, 128, 0, s>>>(g);
+    CTB_LAUNCH_CHECK();
+    x0 = h->staged_in;
+  }
+  // conv_in: Conv1d(idim -> bn, k3, p1) + GELU + Conv1d(bn -> hidden, k3, p1)   (dvae.py:144-148)
+  if ((rc = gemm<GE_GELU>(s, x0, c.idim, M, c.bn_dim, 3 * c.idim, 3, c.idim, 1, 1, F, W + L.in0_w, W + L.in0_b,
+                          nullptr, nullptr, 0, h->bufB, c.bn_dim))) return rc;
+  if ((rc = gemm<GE_BIAS>(s, h->bufB, c.bn_dim, M, c.hidden, 3 * c.bn_dim, 3, c.bn_dim, 1, 1, F, W + L.in2_w,
+                          W + L.in2_b, nullptr, nullptr, 0, h->bufA, c.hidden))) return rc;
+  for (int i = 0; i < c.n_layer; ++i)
+    if ((rc = convnext(s, W, L.blk[i], h->bufA, h->bufB, h->bufH, M, F, c.hidden, 4 * c.hidden, c.dilation))) return rc;
+  // conv_out 1x1 (no bias), out_conv k3 (no bias) * coef        (dvae.py:159,236,289-297)
+  if ((rc = gemm<GE_NONE>(s, h->bufA, c.hidden, M, c.odim, c.hidden, 1, c.hidden, 1, 0, F, W + L.conv_out_w, nullptr,
+                          nullptr, nullptr, 0, h->bufB, c.odim))) return rc;
+  if ((rc = gemm<GE_COEF>(s, h->bufB, c.out_dim, M, MEL_PAD, 3 * c.out_dim, 3, c.out_dim, 1, 1, F, W + L.out_conv_w,
+                          nullptr, W + L.coef, nullptr, 0, h->mel_tm, MEL_PAD))) return rc;
+  if (mel_cf) {
+    dim3 g((F + 31) / 32, (MEL + 31) / 32, B);
+    k_tm_to_cf<<<g, dim3(32, 8), 0, s>>>(h->mel_tm, mel_cf, B, MEL, F, MEL_PAD);
+    CTB_LAUNCH_CHECK();
+  }
+  return CTB_OK;
+}
+
+static int vocos_run(ctb_decoder* h, const float* mel_cf, int B, int F, float* wav, cudaStream_t s) {
+  const ctb_vocos_config& c = h->vc;
+  const VocosOff& L = h->vl;
+  const float* W = h->vW;
+  const int M = B * F, SK = spec_k(c);
+  int rc;
+  if (mel_cf) {
+    dim3 g((F + 31) / 32, (MEL_PAD + 31) / 32, B);
+    k_cf_to_tm<<<g, dim3(32, 8), 0, s>>>(mel_cf, h->mel_tm, B, MEL, F, MEL_PAD);
+    CTB_LAUNCH_CHECK();
+  }
+  // backbone: Conv1d(100 -> dim, k7, p3) -> LN -> ConvNeXt x num_layers -> LN
+  if ((rc = gemm<GE_BIAS>(s, h->mel_tm, MEL_PAD, M, c.dim, 7 * MEL_PAD, 7, MEL_PAD, 1, 3, F, W + L.embed_w,
+                          W + L.embed_b, nullptr, nullptr, 0, h->bufB, c.dim))) return rc;
+  if ((rc = dwln(s, h->bufB, h->bufA, M, F, c.dim, 0, 1, nullptr, nullptr, W + L.norm_w, W + L.norm_b))) return rc;
+  for (int i = 0; i < c.num_layers; ++i)
+    if ((rc = convnext(s, W, L.blk[i], h->bufA, h->bufB, h->bufH, M, F, c.dim, c.intermediate_dim, 1))) return rc;
+  if ((rc = dwln(s, h->bufA, h->bufB, M, F, c.dim, 0, 1, nullptr, nullptr, W + L.fin_w, W + L.fin_b))) return rc;
+  // ISTFTHead: Linear(dim -> n_fft + 2) -> (mag, phase) -> complex spectrum (interleaved re/im)
+  if ((rc = gemm<GE_SPEC>(s, h->bufB, c.dim, M, SK, c.dim, 1, c.dim, 1, 0, F, W + L.head_w, W + L.head_b, nullptr,
+                          nullptr, 0, h->bufA, SK))) return rc;
+  // inverse real DFT * window as a GEMM against the constant basis, then overlap-add / envelope
+  if ((rc = gemm<GE_NONE>(s, h->bufA, SK, M, c.n_fft, SK, 1, SK, 1, 0, F, W + L.basis, nullptr, nullptr, nullptr, 0,
+                          h->bufH, c.n_fft))) return rc;
+  const size_t total = (size_t)B * c.hop_length * (F - 1);
+  k_overlap_add<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(h->bufH, W + L.window, wav, B, F, c.n_fft, c.hop_length);
+  CTB_LAUNCH_CHECK();
+  return CTB_OK;
+}
+
+extern "C" int ctb_dvae_decode(ctb_decoder* h, const void* in_dev, int32_t in_layout, int32_t B, int32_t T,
+                               float* mel_dev, void* stream) {
+  if (!h || !in_dev) return set_err(CTB_ERR_ARG, "null argument");
+  if (!h->dW) return set_err(CTB_ERR_STATE, "handle was created without DVAE weights");
+  if (B < 1 || T < 1 || (size_t)B * 2 * T > h->max_rows)
+    return set_err(CTB_ERR_ARG, "B=%d x T=%d exceeds this handle (max_batch=%d, max_tokens=%d)", B, T, h->max_batch,
+                   h->max_tokens);
+  if (in_layout < 0 || in_layout > 2) return set_err(CTB_ERR_ARG, "bad in_layout");
+  return dvae_run(h, in_dev, in_layout, B, T, mel_dev, (cudaStream_t)stream);
+}
+
+extern "C" int ctb_vocos_decode(ctb_decoder* h, const float* mel_dev, int32_t B, int32_t F, float* wav_dev,
+                                void* stream) {
+  if (!h || !wav_dev) return set_err(CTB_ERR_ARG, "null argument");
+  if (!h->vW) return set_err(CTB_ERR_STATE, "handle was created without Vocos weights");
+  if (B < 1 || F < 2 || (size_t)B * F > h->max_rows) return set_err(CTB_ERR_ARG, "B x F exceeds this handle");
+  return vocos_run(h, mel_dev, B, F, wav_dev, (cudaStream_t)stream);
 }

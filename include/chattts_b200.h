@@ -151,7 +151,8 @@ int ctb_sample(const float* logits_dev, int32_t rows, int32_t V, int32_t rows_pe
 typedef struct ctb_convstack_config {
   int32_t idim, odim, hidden, n_layer, bn_dim, kernel, dilation; /* dvae.py:131-172 */
   int32_t out_dim;    /* DVAE(dim=...) : out_conv input channels; 100 mel bins out (dvae.py:236) */
-  int32_t vq_dim, vq_groups, vq_residual, vq_levels; /* GFSQ (dvae.py:69-97); vq_dim = 0: no VQ layer */
+  int32_t vq_dim, vq_groups, vq_residual; /* GFSQ (dvae.py:69-97); vq_dim = 0: no VQ layer */
+  int32_t vq_levels;  /* low byte: levels per dim (5); bits 8..: residual scale base (0 => levels-1) */
 } ctb_convstack_config;
 
 typedef struct ctb_vocos_config {
@@ -169,13 +170,18 @@ int ctb_decoder_create(const ctb_convstack_config* dvae_cfg, const float* dvae_b
                        int32_t max_tokens, ctb_decoder** out);
 int ctb_decoder_destroy(ctb_decoder* h);
 
-/* DVAE.forward(mode="decode") (dvae.py:276-297):
- *   in_dev: hidden path  [B, C, T] fp32 (C = 2*idim; core.py:519-534 layout), or
- *           code path    [B, num_vq, T] int32 when is_codes != 0 (GFSQ._embed, dvae.py:87-97)
- *   mel_dev [B, 100, 2T] fp32 */
-int ctb_dvae_decode(ctb_decoder* h, const void* in_dev, int32_t is_codes, int32_t B, int32_t T, float* mel_dev,
+/* DVAE.forward(mode="decode") (dvae.py:276-297).  in_layout selects what in_dev holds:
+ *   0: hidden path, channels-first [B, C, T] fp32 (C = 2*idim) - the layout DVAE.__call__ receives
+ *      from core.py:519-534;
+ *   1: hidden path, token-major [B, T, C] fp32 - what ctb_gpt_* writes to hiddens_out_dev; the
+ *      frame doubling of dvae.py:281-287 is then a pure re-interpretation (no copy);
+ *   2: code path, ids [B, num_vq, T] int32 through GFSQ._embed (dvae.py:87-97).
+ *   mel_dev [B, 100, 2T] fp32 channels-first, or NULL to keep the mel only inside the handle
+ *   (time-major) for a following ctb_vocos_decode(mel_dev = NULL). */
+int ctb_dvae_decode(ctb_decoder* h, const void* in_dev, int32_t in_layout, int32_t B, int32_t T, float* mel_dev,
                     void* stream);
-/* Vocos.decode (core.py:505-510): mel [B,100,F] -> wav [B, hop*(F-1)] fp32 */
+/* Vocos.decode (core.py:505-510): mel [B,100,F] channels-first (NULL: the mel left in the handle by
+ * the last ctb_dvae_decode) -> wav [B, hop*(F-1)] fp32 */
 int ctb_vocos_decode(ctb_decoder* h, const float* mel_dev, int32_t B, int32_t F, float* wav_dev, void* stream);
 
 #ifdef __cplusplus

@@ -1,0 +1,98 @@
+"""CPU (torch fp32) restatement of hot path 2: tokens / hidden states -> mel -> waveform.
+
+TEST INFRASTRUCTURE (see oracle/__init__.py).
+
+Pinned against the reference itself: ``dvae_decode`` without VQ (reference ``DVAE.forward``
+decode branch, dvae.py:276-297, ``DVAEDecoder`` :131-172, ``ConvNeXtBlock`` :14-66).
+**Parity unpinned** (third-party code absent from /root/reference, restated from call sites):
+  * ``gfsq_embed``  - vector_quantize_pytorch ``GroupedResidualFSQ.get_output_from_indices``
+    (requirements.txt:6 unpinned; call sites dvae.py:75-80,96).
+  * ``vocos_decode`` - vocos ``VocosBackbone`` + ``ISTFTHead`` (requirements.txt:8 unpinned; call
+    sites core.py:298-317,505-510; head math restated in-tree at examples/onnx/exporter.py:391-405;
+    hyper-parameters config/config.py:74-121).
+"""
+from __future__ import annotations
+
+from typing import Dict
+
+import torch
+import torch.nn.functional as F
+
+State = Dict[str, torch.Tensor]
+
+
+def convnext_block(x: torch.Tensor, s: State, p: str, dilation: int, scale_name: str) -> torch.Tensor:
+    """dvae.py:46-66 (x is [B, C, T]); the Vocos block is the same with dilation 1 / 'gamma'."""
+    C = x.shape[1]
+    y = F.conv1d(x, s[p + "dwconv.weight"], s[p + "dwconv.bias"], padding=dilation * 3, dilation=dilation, groups=C)
+    y = y.transpose(1, 2)
+    y = F.layer_norm(y, (C,), s[p + "norm.weight"], s[p + "norm.bias"], eps=1e-6)
+    y = F.linear(y, s[p + "pwconv1.weight"], s[p + "pwconv1.bias"])
+    y = F.gelu(y)
+    y = F.linear(y, s[p + "pwconv2.weight"], s[p + "pwconv2.bias"])
+    y = y * s[p + scale_name]
+    return y.transpose(1, 2) + x
+
+
+def gfsq_embed(ids: torch.Tensor, s: State, G: int = 2, R: int = 2, levels=(5, 5, 5, 5), scale_base: int = 4
+               ) -> torch.Tensor:
+    """[3p] GFSQ._embed (dvae.py:87-97) -> GroupedResidualFSQ.get_output_from_indices.
+    ids [B, G*R, T] -> feat [B, dim, T].  Codebook c = g*R + r; residual r is scaled by
+    ``scale_base ** -r`` (``levels - 1`` = 4 in the releases ChatTTS was built against)."""
+    B, _, T = ids.shape
+    x = ids.transpose(1, 2).reshape(B, T, G, R).permute(2, 0, 1, 3)  # [G, B, T, R]
+    basis = torch.cumprod(torch.tensor([1] + list(levels[:-1])), 0)
+    lv = torch.tensor(levels)
+    outs = []
+    for g in range(G):
+        z = 0
+        for r in range(R):
+            li = (x[g, :, :, r, None] // basis) % lv        # [B, T, 4] level indices
+            code = (li.float() - (lv // 2).float()) / (lv // 2).float()
+            z = z + code * (float(scale_base) ** -r)
+        outs.append(F.linear(z, s[f"vq_layer.quantizer.rvqs.{g}.project_out.weight"],
+                             s[f"vq_layer.quantizer.rvqs.{g}.project_out.bias"]))
+    return torch.cat(outs, dim=-1).transpose(1, 2)
+
+
+def dvae_decode(inp: torch.Tensor, s: State, *, n_layer: int = 12, has_vq: bool = False, dilation: int = 2,
+                scale_base: int = 4) -> torch.Tensor:
+    """DVAE.forward(mode='decode') (dvae.py:276-297): [B, C, T] (or ids [B,4,T]) -> mel [B, 100, 2T]."""
+    x = gfsq_embed(inp, s, scale_base=scale_base) if has_vq else inp
+    B, C, T = x.shape
+    x = x.view(B, 2, C // 2, T).permute(0, 2, 3, 1).flatten(2)  # frame doubling, dvae.py:281-287
+    y = F.conv1d(x, s["decoder.conv_in.0.weight"], s["decoder.conv_in.0.bias"], padding=1)
+    y = F.gelu(y)
+    y = F.conv1d(y, s["decoder.conv_in.2.weight"], s["decoder.conv_in.2.bias"], padding=1)
+    for i in range(n_layer):
+        y = convnext_block(y, s, f"decoder.decoder_block.{i}.", dilation, "weight")
+    y = F.conv1d(y, s["decoder.conv_out.weight"])
+    y = F.conv1d(y, s["out_conv.weight"], padding=1)
+    return y * s["coef"]
+
+
+def vocos_decode(mel: torch.Tensor, s: State, *, num_layers: int = 8, n_fft: int = 1024, hop: int = 256
+                 ) -> torch.Tensor:
+    """[3p] Vocos.decode = ISTFTHead(VocosBackbone(mel)): mel [B,100,F] -> wav [B, hop*(F-1)]."""
+    x = F.conv1d(mel, s["backbone.embed.weight"], s["backbone.embed.bias"], padding=3)
+    C = x.shape[1]
+    x = F.layer_norm(x.transpose(1, 2), (C,), s["backbone.norm.weight"], s["backbone.norm.bias"], eps=1e-6).transpose(1, 2)
+    for i in range(num_layers):
+        x = convnext_block(x, s, f"backbone.convnext.{i}.", 1, "gamma")
+    x = F.layer_norm(x.transpose(1, 2), (C,), s["backbone.final_layer_norm.weight"],
+                     s["backbone.final_layer_norm.bias"], eps=1e-6)
+    x = F.linear(x, s["head.out.weight"], s["head.out.bias"]).transpose(1, 2)
+    mag, p = x.chunk(2, dim=1)
+    mag = torch.clip(torch.exp(mag), max=1e2)  # examples/onnx/exporter.py:395-398
+    spec = mag * (torch.cos(p) + 1j * torch.sin(p))
+    return torch.istft(spec, n_fft, hop, n_fft, s["head.istft.window"], center=True)
+
+
+def decode_to_wavs(results, use_decoder: bool, dec_state: State, vocos_state: State) -> torch.Tensor:
+    """core.py:512-539: zero-pad ragged per-utterance results to [B, C, maxT], decode, vocode."""
+    maxT = max(int(r.shape[0]) for r in results)
+    batch = torch.zeros(len(results), results[0].shape[1], maxT, dtype=results[0].dtype)
+    for i, r in enumerate(results):
+        batch[i, :, : r.shape[0]] = r.permute(1, 0)
+    mel = dvae_decode(batch, dec_state, has_vq=not use_decoder)
+    return vocos_decode(mel, vocos_state)

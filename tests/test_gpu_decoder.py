@@ -1,0 +1,120 @@
+"""GPU parity of hot path 2 (DVAE decode + Vocos + iSTFT) through the C ABI.
+Tolerances: mel max-abs 1e-4 (fp32 reorder), waveform RMS 1e-4 (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+import torch
+
+from chattts_b200.config import Config
+from chattts_b200.synth import synth_dvae_state, synth_vocos_state
+from oracle import dvae_oracle as O
+
+pytestmark = pytest.mark.gpu
+CFG = Config()
+_c = {}
+
+
+def models():
+    if not _c:
+        from chattts_b200.decoder import DVAE, Vocos
+
+        vs = synth_vocos_state(5)
+        ds = synth_dvae_state(2, CFG.decoder, CFG.decoder.idim)
+        cs = synth_dvae_state(3, CFG.dvae.decoder, CFG.dvae.decoder.idim, CFG.dvae.vq)
+        voc = Vocos(CFG.vocos, "cuda", max_batch=8, max_tokens=256).load_state_dict(vs)
+        dec = DVAE(CFG.decoder, dim=CFG.decoder.idim, device="cuda", vocos=voc, max_batch=8, max_tokens=256)
+        dec.load_state_dict(ds)
+        dv = DVAE(CFG.dvae.decoder, None, CFG.dvae.vq, dim=CFG.dvae.decoder.idim, device="cuda", vocos=voc,
+                  max_batch=8, max_tokens=256)
+        dv.load_state_dict(cs)
+        _c.update(vs=vs, ds=ds, cs=cs, voc=voc, dec=dec, dv=dv)
+    return _c
+
+
+def rms(a, b):
+    return float((a - b).pow(2).mean().sqrt())
+
+
+def test_decoder_hidden_path_reference_fixture():
+    from gpu_util import load_gold
+
+    m = models()
+    g = load_gold("dvae_decoder_hidden")
+    mel = m["dec"](torch.from_numpy(g["x"]))
+    assert mel.shape == (2, 100, 24)
+    assert np.abs(mel.cpu().numpy() - g["mel"]).max() < 1e-4
+
+
+@pytest.mark.parametrize("B,T", [(1, 1), (3, 37), (2, 130)])
+def test_decoder_hidden_path_both_layouts(B, T):
+    m = models()
+    x = torch.randn(B, 768, T, generator=torch.Generator().manual_seed(T))
+    ref = O.dvae_decode(x, m["ds"])
+    mel_cf = m["dec"].engine.dvae_decode(x, 0)
+    mel_tm = m["dec"].engine.dvae_decode(x.permute(0, 2, 1).contiguous(), 1)
+    assert (mel_cf.cpu() - ref).abs().max() < 1e-4
+    assert torch.equal(mel_cf, mel_tm)  # same arithmetic, only the staging differs
+
+
+@pytest.mark.parametrize("B,T", [(1, 2), (4, 61)])
+def test_dvae_code_path(B, T):
+    m = models()
+    ids = torch.randint(0, 625, (B, 4, T), generator=torch.Generator().manual_seed(B))
+    ref = O.dvae_decode(ids, m["cs"], has_vq=True)
+    mel = m["dv"](ids)
+    assert mel.shape == (B, 100, 2 * T)
+    assert (mel.cpu() - ref).abs().max() < 1e-4
+
+
+@pytest.mark.parametrize("B,F", [(1, 2), (2, 9), (3, 150)])
+def test_vocos_waveform_rms(B, F):
+    m = models()
+    mel = torch.randn(B, 100, F, generator=torch.Generator().manual_seed(F)) * 0.5
+    ref = O.vocos_decode(mel, m["vs"])
+    wav = m["voc"].decode(mel)
+    assert wav.shape == (B, 256 * (F - 1))
+    assert rms(wav.cpu(), ref) < 1e-4, rms(wav.cpu(), ref)
+    assert (wav.cpu() - ref).abs().max() < 1e-3
+
+
+@pytest.mark.parametrize("use_decoder", [True, False])
+def test_decode_to_wavs_ragged_batch(use_decoder):
+    """core.py:512-539 semantics incl. zero padding to the batch max length (quirk Q23)."""
+    from chattts_b200.decoder import decode_to_wavs
+
+    m = models()
+    g = torch.Generator().manual_seed(7)
+    lens = [33, 5, 21]
+    if use_decoder:
+        res = [torch.randn(n, 768, generator=g) for n in lens]
+        ref = O.decode_to_wavs(res, True, m["ds"], m["vs"])
+    else:
+        res = [torch.randint(0, 625, (n, 4), generator=g) for n in lens]
+        ref = O.decode_to_wavs(res, False, m["cs"], m["vs"])
+    wav = decode_to_wavs([r.clone() for r in res], use_decoder, m["dec"], m["dv"])
+    assert isinstance(wav, np.ndarray) and wav.dtype == np.float32 and wav.shape == (3, 512 * 33 - 256)
+    assert rms(torch.from_numpy(wav), ref) < 1e-4
+
+
+def test_decode_to_wavs_empty():
+    from chattts_b200.decoder import decode_to_wavs
+
+    m = models()
+    out = decode_to_wavs([], True, m["dec"], m["dv"])
+    assert out.shape == (0,)
+
+
+def test_full_size_properties_10s_batch():
+    """BASELINE configs[3] scale (10 s = 469 tokens) on a small batch: length, finiteness, linearity of
+    the iSTFT stage in the spectrum (zero mel frames at the tail do not leak NaNs), batch-row independence."""
+    from chattts_b200.decoder import DVAE, Vocos
+
+    m = models()
+    voc = Vocos(CFG.vocos, "cuda", max_batch=4, max_tokens=469).load_state_dict(m["vs"])
+    dec = DVAE(CFG.decoder, dim=384, device="cuda", vocos=voc, max_batch=4, max_tokens=469).load_state_dict(m["ds"])
+    x = torch.randn(4, 469, 768, generator=torch.Generator().manual_seed(1))
+    wav = dec.engine.tokens_to_wav(x, 1)
+    assert wav.shape == (4, 512 * 469 - 256) and torch.isfinite(wav).all()
+    solo = dec.engine.tokens_to_wav(x[2:3].contiguous(), 1)
+    assert torch.equal(solo[0], wav[2])  # rows never interact
+    ref = O.vocos_decode(O.dvae_decode(x[:1].permute(0, 2, 1).contiguous(), m["ds"]), m["vs"])
+    assert rms(wav[:1].cpu(), ref) < 1e-4

@@ -55,3 +55,21 @@ def test_embed_prompt_matches(models):
     tmask[0, -2:] = False  # mixed text / code positions (audio prompt splice, tokenizer.py:115-124)
     ids[0, -2:] = torch.randint(0, 626, (2, 4))
     assert torch.equal(embed(ids, tmask), orc.embed_prompt(ids, tmask))
+
+
+def test_dvae_decoder_branch_matches_reference():
+    """DVAE(decoder_config, dim=384) decode branch (the default use_decoder=True path)."""
+    from chattts_b200.config import Config
+    from chattts_b200.synth import synth_dvae_state
+    from oracle.dvae_oracle import dvae_decode
+    from oracle.ref_models import build_reference_dvae
+
+    cfg = Config()
+    st = synth_dvae_state(2, cfg.decoder, cfg.decoder.idim)
+    ref = build_reference_dvae(st, cfg.decoder, cfg.decoder.idim)
+    x = torch.randn(2, 768, 20)
+    with torch.no_grad():
+        want = ref(x.clone(), "decode")
+    got = dvae_decode(x, st)
+    assert want.shape == got.shape == (2, 100, 40)
+    assert (want - got).abs().max() < 1e-5 * max(1.0, float(want.abs().max()))
