@@ -1,0 +1,287 @@
+"""``Chat`` - the public API of the reference (ChatTTS/core.py) re-hosted on the B200 hot paths.
+
+Same surface: ``Chat.load / infer / interrupt / unload / has_loaded / sample_random_speaker``,
+``Chat.RefineTextParams`` / ``Chat.InferCodeParams`` (core.py:137-273).  The two hot paths are
+ours (``GPT.generate`` -> chattts_b200.gpt, ``_decode_to_wavs`` -> chattts_b200.decoder); the
+out-of-scope host components (text normaliser, BERT tokenizer, speaker strings, asset download -
+SURVEY.md 2 rows 7, 8, 10, 11) are *injected*: ``load()`` takes them from an installed reference
+``ChatTTS`` package, ``load_states()`` accepts any objects with the same methods (tests use stubs).
+"""
+from __future__ import annotations
+
+import logging
+import os
+import re
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Union
+
+import numpy as np
+import torch
+
+from .config import Config
+from .decoder import DVAE, Vocos, decode_to_wavs
+from .embed import Embed
+from .gpt import GPT
+from .processors import gen_logits
+
+
+class _IdentityNormalizer:
+    def __call__(self, text, do_text_normalization=True, do_homophone_replacement=True, lang=None):
+        return text
+
+    def register(self, name, normalizer):
+        return True
+
+    def destroy(self):
+        pass
+
+
+class Chat:
+    def __init__(self, logger=logging.getLogger(__name__)):
+        self.logger = logger
+        self.config = Config()
+        self.normalizer = _IdentityNormalizer()
+        self.context = GPT.Context()
+
+    # core.py:49-64
+    def has_loaded(self, use_decoder=False):
+        check = ["vocos", "gpt", "tokenizer", "embed", "decoder" if use_decoder else "dvae"]
+        for module in check:
+            if not hasattr(self, module):
+                self.logger.warning(f"{module} not initialized.")
+                return False
+        return True
+
+    # ------------------------------------------------------------------ loading
+    def load(self, source="local", force_redownload=False, compile: bool = False, custom_path=None,
+             device: Optional[torch.device] = None, coef: Optional[torch.Tensor] = None, use_flash_attn=False,
+             use_vllm=False, experimental: bool = False) -> bool:
+        """core.py:137-163.  ``compile`` / ``use_flash_attn`` / ``use_vllm`` / ``experimental`` are accepted and
+        ignored (one back end).  Asset discovery, tokenizer, normaliser and speaker come
+        from the reference package, which must be importable; weights go through the reference's own loaders
+        (safetensors + ``LlamaModel.from_pretrained``)."""
+        try:
+            import ChatTTS as ref  # the reference package (out-of-scope host components)
+        except Exception as e:  # pragma: no cover - needs the reference + assets
+            raise RuntimeError("Chat.load() needs the reference `ChatTTS` package for asset download, tokenizer, "
+                               "normaliser and speaker handling; use Chat.load_states() for in-memory weights") from e
+        from dataclasses import asdict
+
+        helper = ref.Chat(self.logger)
+        root = helper.download_models(source, force_redownload, custom_path)
+        if root is None:
+            return False
+        paths = {k: os.path.join(root, v) for k, v in asdict(helper.config.path).items()}
+        from safetensors.torch import load_file
+        from transformers import LlamaModel
+
+        gpt_model = LlamaModel.from_pretrained(paths["gpt_ckpt_path"])
+        states = {
+            "gpt": {k: v for k, v in gpt_model.state_dict().items() if not k.startswith("embed_tokens")},
+            "embed": load_file(paths["embed_path"]), "decoder": load_file(paths["decoder_ckpt_path"]),
+            "dvae": load_file(paths["dvae_ckpt_path"]), "vocos": load_file(paths["vocos_ckpt_path"]),
+        }
+        from ChatTTS.model import Speaker, Tokenizer
+
+        dev = device or torch.device("cuda")
+        self.normalizer = helper.normalizer
+        return self.load_states(states, tokenizer=Tokenizer(paths["tokenizer_path"]),
+                                speaker=Speaker(self.config.gpt.hidden_size, helper.config.spk_stat, dev), device=dev,
+                                coef=coef)
+
+    def load_states(self, states: Dict[str, Dict[str, torch.Tensor]], tokenizer, speaker, device=None, coef=None,
+                    max_batch: int = 32, max_context: int = 2560, weights_blob: Optional[torch.Tensor] = None) -> bool:
+        """Build every model from in-memory state dicts (reference names) - core.py:275-384."""
+        device = torch.device(device or "cuda")
+        self.device = self.device_gpt = device
+        cfg = self.config
+        self.vocos = Vocos(cfg.vocos, device, max_batch=max_batch, max_tokens=max_context)
+        self.vocos.state = {k: v.float() for k, v in states["vocos"].items()}
+        self.dvae = DVAE(cfg.dvae.decoder, cfg.dvae.encoder, cfg.dvae.vq, dim=cfg.dvae.decoder.idim, coef=coef,
+                         device=device, vocos=self.vocos, max_batch=max_batch, max_tokens=max_context)
+        self.dvae.load_state_dict(states["dvae"])
+        self.embed = Embed(cfg.embed.hidden_size, cfg.embed.num_audio_tokens, cfg.embed.num_text_tokens,
+                           cfg.embed.num_vq).load_state_dict(states["embed"]).to(device)
+        self.gpt = GPT(cfg.gpt, self.embed, device=device, device_gpt=device, logger=self.logger,
+                       max_batch=max_batch, max_context=max_context)
+        self.gpt.load_state(states.get("gpt"), weights_blob=weights_blob)
+        self.speaker = speaker
+        self.decoder = DVAE(cfg.decoder, dim=cfg.decoder.idim, coef=coef, device=device, vocos=self.vocos,
+                            max_batch=max_batch, max_tokens=max_context)
+        self.decoder.load_state_dict(states["decoder"])
+        self.tokenizer = tokenizer
+        self.coef = coef
+        return self.has_loaded()
+
+    def unload(self):
+        logger = self.logger
+        for module in ["vocos", "gpt", "decoder", "dvae", "tokenizer", "embed", "speaker"]:
+            if hasattr(self, module):
+                delattr(self, module)
+        self.__init__(logger)
+
+    def sample_random_speaker(self) -> str:
+        return self.speaker.sample_random()
+
+    def sample_audio_speaker(self, wav) -> str:
+        raise NotImplementedError("DVAE encode branch (speaker enrolment) is outside the hot path (SURVEY.md 8f N3)")
+
+    # ------------------------------------------------------------------ params (core.py:182-206)
+    @dataclass(repr=False, eq=False)
+    class RefineTextParams:
+        prompt: str = ""
+        top_P: float = 0.7
+        top_K: int = 20
+        temperature: float = 0.7
+        repetition_penalty: float = 1.0
+        max_new_token: int = 384
+        min_new_token: int = 0
+        show_tqdm: bool = True
+        ensure_non_empty: bool = True
+        manual_seed: Optional[int] = None
+
+    @dataclass(repr=False, eq=False)
+    class InferCodeParams(RefineTextParams):
+        prompt: str = "[speed_5]"
+        spk_emb: Optional[str] = None
+        spk_smp: Optional[str] = None
+        txt_smp: Optional[str] = None
+        temperature: float = 0.3
+        repetition_penalty: float = 1.05
+        max_new_token: int = 2048
+        stream_batch: int = 24
+        stream_speed: int = 12000
+        pass_first_n_batches: int = 2
+
+    # ------------------------------------------------------------------ infer (core.py:208-270)
+    def infer(self, text, stream=False, lang=None, skip_refine_text=False, refine_text_only=False, use_decoder=True,
+              do_text_normalization=True, do_homophone_replacement=True, split_text=True, max_split_batch=4,
+              params_refine_text=None, params_infer_code=None):
+        params_refine_text = params_refine_text or Chat.RefineTextParams()
+        params_infer_code = params_infer_code or Chat.InferCodeParams()
+        self.context.set(False)
+        if split_text and isinstance(text, str):
+            if "\n" in text:
+                text = text.split("\n")
+            else:
+                text = [t for t in re.split(r"(?<=。)|(?<=\.\s)", text) if t]
+            self.logger.info("split text into %d parts", len(text))
+        if len(text) == 0:
+            return []
+        res_gen = self._infer(text, stream, lang, skip_refine_text, refine_text_only, use_decoder,
+                              do_text_normalization, do_homophone_replacement, split_text, max_split_batch,
+                              params_refine_text, params_infer_code)
+        if stream:
+            return res_gen
+        if not refine_text_only:
+            stripped = []
+            thr = np.float32(1e-5)
+            for wavs in res_gen:
+                for wav in wavs:
+                    stripped.append(wav[np.abs(wav) > thr])  # quirk Q20
+            if split_text:
+                return [np.concatenate(stripped)]
+            return stripped
+        return next(res_gen)
+
+    def interrupt(self):
+        self.context.set(True)
+
+    # core.py:386-503
+    def _infer(self, text, stream, lang, skip_refine_text, refine_text_only, use_decoder, do_text_normalization,
+               do_homophone_replacement, split_text, max_split_batch, params_refine_text, params_infer_code):
+        assert self.has_loaded(use_decoder=use_decoder)
+        if not isinstance(text, list):
+            text = [text]
+        text = [self.normalizer(t, do_text_normalization, do_homophone_replacement, lang) for t in text]
+        if not skip_refine_text:
+            refined = self._refine_text(text, self.device, params_refine_text)
+            tokens = [i[i.less(self.tokenizer.break_0_ids)] for i in refined.ids]
+            text = self.tokenizer.decode(tokens)
+            refined.destroy()
+            if refine_text_only:
+                if split_text and isinstance(text, list):
+                    text = "\n".join(text)
+                yield text
+                return
+        if split_text and len(text) > 1 and params_infer_code.spk_smp is None:
+            # core.py:435-453 samples a speaker from sentence 0 via the DVAE *encode* branch (out of the hot
+            # path): not rebuilt - pass spk_smp / spk_emb explicitly or split_text=False.
+            self.logger.warning("auto speaker sampling from the first sentence is not available; "
+                                "sentences are generated without a sampled speaker prompt")
+        if stream:
+            length, pass_batch_count = 0, 0
+        if split_text:
+            n = (len(text) + max_split_batch - 1) // max_split_batch
+        else:
+            n, max_split_batch = 1, len(text)
+        for i in range(n):
+            chunk = text[i * max_split_batch: (i + 1) * max_split_batch]
+            for result in self._infer_code(chunk, stream, self.device, use_decoder, params_infer_code):
+                wavs = self._decode_to_wavs(result.hiddens if use_decoder else result.ids, use_decoder)
+                result.destroy()
+                if stream:
+                    pass_batch_count += 1
+                    if pass_batch_count <= params_infer_code.pass_first_n_batches:
+                        continue
+                    a, b = length, min(length + params_infer_code.stream_speed, wavs.shape[1])
+                    length = b
+                    yield wavs[:, a:b]
+                else:
+                    yield wavs
+            if stream:
+                new_wavs = wavs[:, length:]
+                keep = np.sum(np.abs(new_wavs) > 1e-5, axis=0) > 0
+                yield new_wavs[:][:, keep]
+
+    # core.py:512-539 - hot path 2
+    @torch.inference_mode()
+    def _decode_to_wavs(self, result_list: List[torch.Tensor], use_decoder: bool):
+        return decode_to_wavs(result_list, use_decoder, self.decoder, self.dvae)
+
+    def _vocos_decode(self, spec: torch.Tensor) -> np.ndarray:
+        return self.vocos_engine().vocos_decode(spec).cpu().numpy()
+
+    def vocos_engine(self):
+        return self.decoder.engine
+
+    # core.py:541-662 - hot path 1 (audio codes)
+    @torch.no_grad()
+    def _infer_code(self, text, stream: bool, device, return_hidden: bool, params):
+        if not isinstance(text, list):
+            text = [text]
+        assert len(text), "text should not be empty"
+        temperature = params.temperature if isinstance(params.temperature, list) else [params.temperature] * self.config.gpt.num_vq
+        input_ids, attention_mask, text_mask = self.tokenizer.encode(
+            self.speaker.decorate_code_prompts(text, params.prompt, params.txt_smp, params.spk_emb),
+            self.config.gpt.num_vq,
+            prompt=(self.speaker.decode_prompt(params.spk_smp) if params.spk_smp is not None else None),
+            device=self.device_gpt)
+        num_code = self.config.gpt.num_audio_tokens - 1
+        warpers, processors = gen_logits(num_code=num_code, top_P=params.top_P, top_K=params.top_K,
+                                         repetition_penalty=params.repetition_penalty)
+        emb = self.embed(input_ids, text_mask)
+        if params.spk_emb is not None:
+            self.speaker.apply(emb, params.spk_emb, input_ids, self.tokenizer.spk_emb_ids, self.gpt.device_gpt)
+        return self.gpt.generate(
+            emb, input_ids, temperature=torch.tensor(temperature), eos_token=num_code, attention_mask=attention_mask,
+            max_new_token=params.max_new_token, min_new_token=params.min_new_token,
+            logits_processors=(*processors, *warpers), infer_text=False, return_hidden=return_hidden, stream=stream,
+            show_tqdm=params.show_tqdm, ensure_non_empty=params.ensure_non_empty, stream_batch=params.stream_batch,
+            manual_seed=params.manual_seed, context=self.context)
+
+    # core.py:664-751 - hot path 1 (text refinement)
+    @torch.no_grad()
+    def _refine_text(self, text, device, params):
+        if not isinstance(text, list):
+            text = [text]
+        input_ids, attention_mask, text_mask = self.tokenizer.encode(
+            self.speaker.decorate_text_prompts(text, params.prompt), self.config.gpt.num_vq, device=self.device_gpt)
+        warpers, processors = gen_logits(num_code=self.tokenizer.len, top_P=params.top_P, top_K=params.top_K,
+                                         repetition_penalty=params.repetition_penalty)
+        emb = self.embed(input_ids, text_mask)
+        return next(self.gpt.generate(
+            emb, input_ids, temperature=torch.tensor([params.temperature]), eos_token=self.tokenizer.eos_token,
+            attention_mask=attention_mask, max_new_token=params.max_new_token, min_new_token=params.min_new_token,
+            logits_processors=(*processors, *warpers), infer_text=True, stream=False, show_tqdm=params.show_tqdm,
+            ensure_non_empty=params.ensure_non_empty, manual_seed=params.manual_seed, context=self.context))

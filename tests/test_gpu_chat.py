@@ -1,0 +1,64 @@
+"""API-compat test of the re-hosted ``Chat`` (core.py surface) end to end on the GPU with stub
+tokenizer/speaker: infer() -> List[np.ndarray], streaming generator, refine_text_only, interrupt."""
+import numpy as np
+import pytest
+import torch
+
+from chattts_b200.synth import synth_all
+
+pytestmark = pytest.mark.gpu
+_c = {}
+
+
+def chat():
+    if not _c:
+        from chattts_b200 import Chat
+        from stubs import StubSpeaker, StubTokenizer
+
+        c = Chat()
+        assert not c.has_loaded()
+        assert c.load_states(synth_all(0), tokenizer=StubTokenizer(), speaker=StubSpeaker(), device="cuda",
+                             max_batch=4, max_context=256)
+        _c["chat"] = c
+    return _c["chat"]
+
+
+def test_infer_returns_waveforms_and_is_deterministic_under_seed():
+    c = chat()
+    p = c.InferCodeParams(manual_seed=3, max_new_token=40, min_new_token=20, show_tqdm=False)
+    a = c.infer(["hello there", "hi"], skip_refine_text=True, split_text=False, params_infer_code=p)
+    b = c.infer(["hello there", "hi"], skip_refine_text=True, split_text=False, params_infer_code=p)
+    assert len(a) == 2 and all(isinstance(w, np.ndarray) and w.dtype == np.float32 and w.ndim == 1 for w in a)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    assert all(len(w) > 0 and np.isfinite(w).all() for w in a)
+
+
+def test_code_path_use_decoder_false():
+    c = chat()
+    p = c.InferCodeParams(manual_seed=3, max_new_token=24, min_new_token=24, show_tqdm=False)
+    out = c.infer(["abc"], skip_refine_text=True, split_text=False, use_decoder=False, params_infer_code=p)
+    assert len(out) == 1 and out[0].size > 0
+
+
+def test_refine_text_only_returns_text():
+    c = chat()
+    r = c.RefineTextParams(manual_seed=5, max_new_token=12, show_tqdm=False)
+    out = c.infer(["some text"], refine_text_only=True, split_text=False, params_refine_text=r)
+    assert isinstance(out, list) and isinstance(out[0], str)
+
+
+def test_streaming_generator_yields_arrays():
+    c = chat()
+    p = c.InferCodeParams(manual_seed=3, max_new_token=100, min_new_token=100, show_tqdm=False)
+    chunks = list(c.infer(["stream me"], stream=True, skip_refine_text=True, split_text=False, params_infer_code=p))
+    assert len(chunks) >= 2 and all(ch.ndim == 2 and ch.shape[0] == 1 for ch in chunks)
+
+
+def test_interrupt_stops_generation():
+    c = chat()
+    p = c.InferCodeParams(manual_seed=3, max_new_token=200, min_new_token=200, show_tqdm=False)
+    gen = c._infer_code(["abc"], False, c.device, True, p)
+    c.context.set(True)
+    out = list(gen)[-1]
+    assert out.ids[0].shape[0] < 200
+    c.context.set(False)
