@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include <atomic>
+#include <utility>
 
 #include "../../include/chattts_b200.h"
 
@@ -33,7 +34,26 @@ int set_err(int code, const char* fmt, ...);
                             cudaGetErrorString(_e));                                        \
   } while (0)
 
-constexpr int kPageTokens = 16;  // KV page = 16 tokens (the reference's vLLM fork: velocity/configs.py:567)
+constexpr int kPageTokens = 16;
+
+// Programmatic dependent launch (PDL): every kernel of the decode step is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization.  A kernel calls pdl_trigger() first (lets the
+// next kernel's CTAs become resident and prefetch their weights) and pdl_wait() before it touches
+// anything a previous kernel wrote (griddepcontrol.wait = predecessors complete + memory visible).
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}  // KV page = 16 tokens (the reference's vLLM fork: velocity/configs.py:567)
 
 // ---------------------------------------------------------------- device helpers
 __device__ __forceinline__ float4 ldg_stream(const float4* p) {
@@ -44,6 +64,13 @@ __device__ __forceinline__ float4 ldg_stream(const float4* p) {
                : "l"(p));
   return r;
 }
+
+// Activations / loop state / KV written by earlier kernels: L2-coherent loads only.  With PDL a CTA
+// can be resident while its predecessors still run, so nothing mutable may be served from L1.
+__device__ __forceinline__ float4 ldg_cg(const float4* p) { return __ldcg(p); }
+__device__ __forceinline__ float ldg_cg(const float* p) { return __ldcg(p); }
+__device__ __forceinline__ int ldg_cg(const int* p) { return __ldcg(p); }
+__device__ __forceinline__ int ldg_cg(const uint8_t* p) { return (int)__ldcg(p); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -164,7 +164,7 @@ static int launch_gemv_t(const GemvP& p, int ntiles, cudaStream_t s) {
     attr_done = true;
   }
   dim3 grid((p.ntasks + GEMV_WARPS - 1) / GEMV_WARPS, ntiles);
-  k_gemv<BT, EPI><<<grid, GEMV_WARPS * 32, smem, s>>>(p);
+  CTB_CUDA(launch_pdl(k_gemv<BT, EPI>, grid, dim3(GEMV_WARPS * 32), smem, s, p));
   CTB_LAUNCH_CHECK();
   return CTB_OK;
 }
@@ -188,7 +188,7 @@ static int launch_sample(const SampleP& sp, cudaStream_t s) {
     CTB_CUDA(cudaFuncSetAttribute(k_sample, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_max = smem;
   }
-  k_sample<<<sp.rows, SAMPLE_THREADS, smem, s>>>(sp);
+  CTB_CUDA(launch_pdl(k_sample, dim3(sp.rows), dim3(SAMPLE_THREADS), smem, s, sp));
   CTB_LAUNCH_CHECK();
   return CTB_OK;
 }
@@ -238,7 +238,7 @@ static int launch_layer_kernel(ctb_gpt* h, const StepCtx& x, int l, int kind, cu
       // context after this call <= T0 + max_new: only launch splits that can be populated
       const int max_ctx = std::min(c.max_context, h->T0 + h->max_new);
       dim3 agrid((max_ctx + ATT_CHUNK - 1) / ATT_CHUNK, c.num_heads, h->B);
-      k_attn<<<agrid, ATT_THREADS, 0, s>>>(a);
+      CTB_CUDA(launch_pdl(k_attn, agrid, dim3(ATT_THREADS), 0, s, a));
       CTB_LAUNCH_CHECK();
       return CTB_OK;
     }
@@ -294,7 +294,7 @@ static int enqueue_step(ctb_gpt* h, int col, bool sample, cudaStream_t s) {
   ip.ids_out = h->ids_out; ip.max_new = h->max_new; ip.num_vq = c.num_vq; ip.num_audio = c.num_audio_tokens;
   ip.infer_text = h->infer_text;
   ip.x = h->x; ip.seq_len = h->seq_len; ip.pos = h->pos; ip.active = h->active;
-  k_input<<<h->B, 256, 0, s>>>(ip);
+  CTB_CUDA(launch_pdl(k_input, dim3(h->B), dim3(256), 0, s, ip));
   CTB_LAUNCH_CHECK();
 
   const StepCtx x = make_ctx(h, decode);
@@ -309,7 +309,7 @@ static int enqueue_step(ctb_gpt* h, int col, bool sample, cudaStream_t s) {
   fp.st = h->st; fp.B = h->B; fp.rows_per_item = h->infer_text ? 1 : c.num_vq; fp.num_vq = c.num_vq;
   fp.max_new = h->max_new; fp.eos = h->sampler.eos_token; fp.idx = h->idx; fp.ids_out = h->ids_out;
   fp.finish = h->finish; fp.end_idx = h->end_idx;
-  k_finalize<<<1, 256, 0, s>>>(fp);
+  CTB_CUDA(launch_pdl(k_finalize, dim3(1), dim3(256), 0, s, fp));
   CTB_LAUNCH_CHECK();
   return CTB_OK;
 }

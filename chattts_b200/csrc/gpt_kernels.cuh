@@ -21,7 +21,7 @@ struct LoopState {
 
 constexpr int KC = 768;        // K chunk staged in shared memory (= hidden size of the model)
 constexpr int GEMV_WARPS = 8;  // warps per CTA, one 2-row task per warp
-constexpr int ATT_CHUNK = 128; // tokens per attention CTA (flash-decoding split)
+constexpr int ATT_CHUNK = 64;  // tokens per attention CTA (flash-decoding split)
 constexpr int ATT_THREADS = 128;
 
 enum Epi { EPI_QKV = 0, EPI_OPROJ = 1, EPI_GATEUP = 2, EPI_DOWN = 3, EPI_HEADS = 4 };
@@ -62,7 +62,7 @@ __device__ __forceinline__ size_t kv_off(int page, int which, int h, int slot, i
 
 template <int BT, int EPI>
 __global__ void __launch_bounds__(GEMV_WARPS * 32) k_gemv(const GemvP p) {
-  if (p.check_finished && p.st->all_finished) return;
+  pdl_trigger();
   extern __shared__ __align__(16) float xs[];  // [BT][KC]
   __shared__ float rinv[BT];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -106,6 +106,8 @@ __global__ void __launch_bounds__(GEMV_WARPS * 32) k_gemv(const GemvP p) {
 #pragma unroll
     for (int i = 0; i < 6; ++i) { w0[i] = ldg_stream(w0p + i * 32); w1[i] = ldg_stream(w1p + i * 32); }
   }
+  pdl_wait();  // everything below reads activations / loop state written by earlier kernels
+  if (p.check_finished && ldg_cg(&p.st->all_finished)) return;
 
   for (int c = 0; c < nchunks; ++c) {
     if (c > 0) __syncthreads();
@@ -113,7 +115,7 @@ __global__ void __launch_bounds__(GEMV_WARPS * 32) k_gemv(const GemvP p) {
     for (int i = tid; i < BT * (KC / 4); i += GEMV_WARPS * 32) {
       const int b = i / (KC / 4), k4 = i % (KC / 4);
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (b < nb) v = *reinterpret_cast<const float4*>(p.xin + (size_t)(bbase + b) * p.K + c * KC + k4 * 4);
+      if (b < nb) v = ldg_cg(reinterpret_cast<const float4*>(p.xin + (size_t)(bbase + b) * p.K + c * KC + k4 * 4));
       reinterpret_cast<float4*>(xs)[i] = v;
     }
     __syncthreads();
@@ -133,7 +135,7 @@ __global__ void __launch_bounds__(GEMV_WARPS * 32) k_gemv(const GemvP p) {
       __syncthreads();
       if (EPI == EPI_HEADS && p.hidden_out != nullptr && blockIdx.x == 0) {
         // last_hidden_state of this step (gpt.py:430-436), written once
-        const int step = p.st->n_gen;
+        const int step = ldg_cg(&p.st->n_gen);
         for (int i = tid; i < nb * KC; i += GEMV_WARPS * 32) {
           const int b = i / KC, k = i % KC;
           p.hidden_out[(size_t)(bbase + b) * p.hidden_stride + (size_t)step * KC + k] = xs[i];
@@ -177,14 +179,14 @@ __global__ void __launch_bounds__(GEMV_WARPS * 32) k_gemv(const GemvP p) {
   const float v0 = acc0[0], v1 = acc1[0];
 
   if (EPI == EPI_QKV) {
-    if (!p.active[b]) return;
+    if (!ldg_cg(&p.active[b])) return;
     const int half = p.hd / 2;
     const int nq = p.Hq * half, nk = p.Hkv * half;
     int t = task, which = 0;
     if (t >= nq + nk) { which = 2; t -= nq + nk; }
     else if (t >= nq) { which = 1; t -= nq; }
     const int h = t / half, j = t % half;
-    const int pos = p.pos[b];
+    const int pos = ldg_cg(&p.pos[b]);
     float o0 = v0, o1 = v1;
     if (which < 2) {
       // HF apply_rotary_pos_emb: q*cos + rotate_half(q)*sin, each product rounded separately
@@ -203,8 +205,8 @@ __global__ void __launch_bounds__(GEMV_WARPS * 32) k_gemv(const GemvP p) {
     }
   } else if (EPI == EPI_OPROJ || EPI == EPI_DOWN) {
     const int d = p.nrows;
-    p.xres[(size_t)b * d + r0] = __fadd_rn(p.xres[(size_t)b * d + r0], v0);
-    if (r1_valid) p.xres[(size_t)b * d + r1] = __fadd_rn(p.xres[(size_t)b * d + r1], v1);
+    p.xres[(size_t)b * d + r0] = __fadd_rn(ldg_cg(&p.xres[(size_t)b * d + r0]), v0);
+    if (r1_valid) p.xres[(size_t)b * d + r1] = __fadd_rn(ldg_cg(&p.xres[(size_t)b * d + r1]), v1);
   } else if (EPI == EPI_GATEUP) {
     // LlamaMLP: silu(gate) * up ; silu(x) = x / (1 + exp(-x))
     const float sg = __fdiv_rn(v0, __fadd_rn(1.0f, expf(-v0)));
@@ -239,7 +241,9 @@ struct InputP {
 #ifdef CTB_GPT_KERNELS_IMPL
 __global__ void k_input(const InputP p) {
   const int b = blockIdx.x;
-  if (p.decode && p.st->all_finished) return;
+  pdl_trigger();
+  pdl_wait();
+  if (p.decode && ldg_cg(&p.st->all_finished)) return;
   float* x = p.x + (size_t)b * p.d;
   bool act;
   if (!p.decode) {
@@ -248,21 +252,23 @@ __global__ void k_input(const InputP p) {
     for (int k = threadIdx.x; k < p.d; k += blockDim.x) x[k] = act ? e[k] : 0.f;
   } else {
     act = true;
-    const int32_t* id = p.ids_out + ((size_t)b * p.max_new + (p.st->n_gen - 1)) * p.num_vq;
+    const int32_t* id = p.ids_out + ((size_t)b * p.max_new + (ldg_cg(&p.st->n_gen) - 1)) * p.num_vq;
     if (p.infer_text) {
-      const float* e = p.emb_text + (size_t)id[0] * p.d;
+      const float* e = p.emb_text + (size_t)ldg_cg(&id[0]) * p.d;
       for (int k = threadIdx.x; k < p.d; k += blockDim.x) x[k] = e[k];
     } else {
       // gpt.py:409-413: stack(code_emb, 3).sum(3)
+      int idq[8];
+      for (int q = 0; q < p.num_vq; ++q) idq[q] = ldg_cg(&id[q]);
       for (int k = threadIdx.x; k < p.d; k += blockDim.x) {
         float s = 0.f;
-        for (int q = 0; q < p.num_vq; ++q) s += p.emb_code[((size_t)q * p.num_audio + id[q]) * p.d + k];
+        for (int q = 0; q < p.num_vq; ++q) s += p.emb_code[((size_t)q * p.num_audio + idq[q]) * p.d + k];
         x[k] = s;
       }
     }
   }
   if (threadIdx.x == 0) {
-    const int n = p.seq_len[b];
+    const int n = ldg_cg(&p.seq_len[b]);
     p.pos[b] = n;               // position id = #valid tokens before this one (gpt.py:234-241)
     p.active[b] = act ? 1 : 0;
     if (act) p.seq_len[b] = n + 1;
@@ -285,83 +291,108 @@ struct AttnP {
   float scaling;
 };
 
-// grid (nsplit_max, Hq, B); block ATT_THREADS.  hd == 64 assumed (checked on the host).
+// grid (nsplit_max, Hq, B); block ATT_THREADS (4 warps).  hd == 64 (checked on the host).
+// Each warp owns ATT_CHUNK/4 keys of the CTA's chunk: 8 lanes per key row, all K and V rows of the warp
+// are requested up front (one memory round trip), softmax statistics stay in registers; the four warps
+// merge through shared memory and the CTA publishes (m, l, o[64]); the last CTA of a (row, head)
+// merges the splits (flash-decoding).
 #ifdef CTB_GPT_KERNELS_IMPL
 __global__ void __launch_bounds__(ATT_THREADS) k_attn(const AttnP p) {
-  if (p.check_finished && p.st->all_finished) return;
+  pdl_trigger();
+  pdl_wait();
+  if (p.check_finished && ldg_cg(&p.st->all_finished)) return;
   const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int HD = 64;
+  constexpr int HD = 64, NW = ATT_THREADS / 32, PER_WARP = ATT_CHUNK / NW, ITER = PER_WARP / 4;
   float* outp = p.out + (size_t)b * p.Hq * HD + h * HD;
-  if (!p.active[b]) { if (split == 0 && tid < HD) outp[tid] = 0.f; return; }
-  const int n = p.pos[b] + 1;  // keys 0..pos
+  if (!ldg_cg(&p.active[b])) { if (split == 0 && tid < HD) outp[tid] = 0.f; return; }
+  const int n = ldg_cg(&p.pos[b]) + 1;  // keys 0..pos
   const int nsplit = (n + ATT_CHUNK - 1) / ATT_CHUNK;
   if (split >= nsplit) return;
-  const int t0 = split * ATT_CHUNK, t1 = min(n, t0 + ATT_CHUNK);
   const int hk = h / (p.Hq / p.Hkv);
   const int* bt = p.block_table + b * p.pages_per_row;
+  const int sub = lane & 7, grp = lane >> 3;
 
-  __shared__ float s_p[ATT_CHUNK];
-  __shared__ float s_red[ATT_THREADS / 32];
-  __shared__ float s_o[ATT_THREADS / 16][HD];
+  __shared__ float s_m[NW], s_l[NW];
+  __shared__ __align__(16) float s_o[NW][HD];
   __shared__ int s_last;
 
-  // ---- scores: 8 lanes per key row (two float4 each), 4 keys per warp instruction
-  const int sub = lane & 7;
-  const float4 q0 = *reinterpret_cast<const float4*>(p.q + (size_t)b * p.Hq * HD + h * HD + sub * 8);
-  const float4 q1 = *reinterpret_cast<const float4*>(p.q + (size_t)b * p.Hq * HD + h * HD + sub * 8 + 4);
-  for (int t = t0 + warp * 4 + (lane >> 3); t < t0 + ATT_CHUNK; t += (ATT_THREADS / 32) * 4) {
-    float s = 0.f;
-    if (t < t1) {
-      const float* kr = p.kv + kv_off(bt[t / kPageTokens], 0, hk, t % kPageTokens, p.Hkv, HD) + sub * 8;
-      const float4 k0 = ldg_stream(reinterpret_cast<const float4*>(kr));
-      const float4 k1 = ldg_stream(reinterpret_cast<const float4*>(kr + 4));
-      s = q0.x * k0.x + q0.y * k0.y + q0.z * k0.z + q0.w * k0.w + q1.x * k1.x + q1.y * k1.y + q1.z * k1.z + q1.w * k1.w;
+  const float* qp = p.q + (size_t)b * p.Hq * HD + h * HD + sub * 8;
+  const float4 q0 = ldg_cg(reinterpret_cast<const float4*>(qp));
+  const float4 q1 = ldg_cg(reinterpret_cast<const float4*>(qp + 4));
+  const int tbase = split * ATT_CHUNK + warp * PER_WARP + grp;
+  float4 k0[ITER], k1[ITER], v0[ITER], v1[ITER];
+#pragma unroll
+  for (int i = 0; i < ITER; ++i) {
+    const int t = tbase + 4 * i;
+    k0[i] = k1[i] = v0[i] = v1[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t < n) {
+      const int page = bt[t / kPageTokens];
+      const float* kr = p.kv + kv_off(page, 0, hk, t % kPageTokens, p.Hkv, HD) + sub * 8;
+      const float* vr = p.kv + kv_off(page, 1, hk, t % kPageTokens, p.Hkv, HD) + sub * 8;
+      k0[i] = ldg_cg(reinterpret_cast<const float4*>(kr));
+      k1[i] = ldg_cg(reinterpret_cast<const float4*>(kr + 4));
+      v0[i] = ldg_cg(reinterpret_cast<const float4*>(vr));
+      v1[i] = ldg_cg(reinterpret_cast<const float4*>(vr + 4));
     }
+  }
+  float sc[ITER], m = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < ITER; ++i) {
+    float s = q0.x * k0[i].x + q0.y * k0[i].y + q0.z * k0[i].z + q0.w * k0[i].w + q1.x * k1[i].x + q1.y * k1[i].y +
+              q1.z * k1[i].z + q1.w * k1[i].w;
     s += __shfl_xor_sync(0xffffffffu, s, 1);
     s += __shfl_xor_sync(0xffffffffu, s, 2);
     s += __shfl_xor_sync(0xffffffffu, s, 4);
-    if (sub == 0 && t < t1) s_p[t - t0] = s * p.scaling;
+    sc[i] = (tbase + 4 * i < n) ? s * p.scaling : -INFINITY;
+    m = fmaxf(m, sc[i]);
+  }
+  m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
+  m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 16));
+  float l = 0.f, o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (m > -INFINITY) {
+#pragma unroll
+    for (int i = 0; i < ITER; ++i) {
+      const float e = expf(sc[i] - m);  // exp(-inf) = 0 for masked keys
+      l += e;
+      o[0] = fmaf(e, v0[i].x, o[0]); o[1] = fmaf(e, v0[i].y, o[1]); o[2] = fmaf(e, v0[i].z, o[2]);
+      o[3] = fmaf(e, v0[i].w, o[3]); o[4] = fmaf(e, v1[i].x, o[4]); o[5] = fmaf(e, v1[i].y, o[5]);
+      o[6] = fmaf(e, v1[i].z, o[6]); o[7] = fmaf(e, v1[i].w, o[7]);
+    }
+  }
+  // merge the 4 key groups of the warp (same `sub`, different `grp`)
+  l += __shfl_xor_sync(0xffffffffu, l, 8);
+  l += __shfl_xor_sync(0xffffffffu, l, 16);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    o[j] += __shfl_xor_sync(0xffffffffu, o[j], 8);
+    o[j] += __shfl_xor_sync(0xffffffffu, o[j], 16);
+  }
+  if (lane < 8) {
+    *reinterpret_cast<float4*>(&s_o[warp][lane * 8]) = make_float4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<float4*>(&s_o[warp][lane * 8 + 4]) = make_float4(o[4], o[5], o[6], o[7]);
+    if (lane == 0) { s_m[warp] = m; s_l[warp] = l; }
   }
   __syncthreads();
-  // ---- chunk max / exp / sum
-  float m = -INFINITY;
-  for (int i = tid; i < t1 - t0; i += ATT_THREADS) m = fmaxf(m, s_p[i]);
-  m = warp_max(m);
-  if (lane == 0) s_red[warp] = m;
-  __syncthreads();
-  m = fmaxf(fmaxf(s_red[0], s_red[1]), fmaxf(s_red[2], s_red[3]));
-  __syncthreads();
-  float l = 0.f;
-  for (int i = tid; i < t1 - t0; i += ATT_THREADS) { const float e = expf(s_p[i] - m); s_p[i] = e; l += e; }
-  l = warp_sum(l);
-  if (lane == 0) s_red[warp] = l;
-  __syncthreads();
-  l = (s_red[0] + s_red[1]) + (s_red[2] + s_red[3]);
-  // ---- P.V : thread (tg, d4): tokens tg, tg+8, ... ; dims 4*d4..4*d4+3
-  const int tg = tid >> 4, d4 = tid & 15;
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int t = t0 + tg; t < t1; t += ATT_THREADS / 16) {
-    const float* vr = p.kv + kv_off(bt[t / kPageTokens], 1, hk, t % kPageTokens, p.Hkv, HD) + d4 * 4;
-    const float4 v = ldg_stream(reinterpret_cast<const float4*>(vr));
-    const float w = s_p[t - t0];
-    acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y); acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
-  }
-  *reinterpret_cast<float4*>(&s_o[tg][d4 * 4]) = acc;
-  __syncthreads();
-  float o = 0.f;
+  // ---- merge the warps: thread d < 64 owns output dim d
+  float M = -INFINITY, L = 0.f, O = 0.f;
   if (tid < HD) {
 #pragma unroll
-    for (int g = 0; g < ATT_THREADS / 16; ++g) o += s_o[g][tid];
+    for (int w = 0; w < NW; ++w) M = fmaxf(M, s_m[w]);
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+      const float f = (s_m[w] > -INFINITY) ? expf(s_m[w] - M) : 0.f;
+      L = fmaf(f, s_l[w], L);
+      O = fmaf(f, s_o[w][tid], O);
+    }
   }
   if (nsplit == 1) {
-    if (tid < HD) outp[tid] = o / l;
+    if (tid < HD) outp[tid] = O / L;
     return;
   }
-  // ---- flash-decoding combine: the last CTA of this (b, h) merges the partials
   float* part = p.part + (((size_t)b * p.Hq + h) * p.nsplit_max + split) * (HD + 2);
-  if (tid < HD) part[tid] = o;
-  if (tid == 0) { part[HD] = m; part[HD + 1] = l; }
+  if (tid < HD) part[tid] = O;
+  if (tid == 0) { part[HD] = M; part[HD + 1] = L; }
   __threadfence();
   __syncthreads();
   if (tid == 0) s_last = (atomicAdd(&p.counter[b * p.Hq + h], 1) == nsplit - 1);
@@ -369,18 +400,17 @@ __global__ void __launch_bounds__(ATT_THREADS) k_attn(const AttnP p) {
   if (!s_last) return;
   __threadfence();
   const float* pb = p.part + (((size_t)b * p.Hq + h) * p.nsplit_max) * (HD + 2);
-  float M = -INFINITY;
-  for (int s = 0; s < nsplit; ++s) M = fmaxf(M, __ldcg(pb + s * (HD + 2) + HD));
-  float L = 0.f, O = 0.f;
+  float GM = -INFINITY;
+  for (int s = 0; s < nsplit; ++s) GM = fmaxf(GM, __ldcg(pb + s * (HD + 2) + HD));
+  float GL = 0.f, GO = 0.f;
   for (int s = 0; s < nsplit; ++s) {
-    const float w = expf(__ldcg(pb + s * (HD + 2) + HD) - M);
-    L = fmaf(w, __ldcg(pb + s * (HD + 2) + HD + 1), L);
-    if (tid < HD) O = fmaf(w, __ldcg(pb + s * (HD + 2) + tid), O);
+    const float w = expf(__ldcg(pb + s * (HD + 2) + HD) - GM);
+    GL = fmaf(w, __ldcg(pb + s * (HD + 2) + HD + 1), GL);
+    if (tid < HD) GO = fmaf(w, __ldcg(pb + s * (HD + 2) + tid), GO);
   }
-  if (tid < HD) outp[tid] = O / L;
+  if (tid < HD) outp[tid] = GO / GL;
   if (tid == 0) p.counter[b * p.Hq + h] = 0;
 }
-
 #endif  // CTB_GPT_KERNELS_IMPL
 
 // ------------------------------------------------------------------ sampler

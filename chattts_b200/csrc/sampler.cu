@@ -61,7 +61,9 @@ __device__ float philox_exp1(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c
 }  // namespace
 
 __global__ void __launch_bounds__(SAMPLE_THREADS) k_sample(const SampleP p) {
-  if (p.check_finished && p.st->all_finished) return;
+  pdl_trigger();
+  pdl_wait();
+  if (p.check_finished && ldg_cg(&p.st->all_finished)) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* s_x = reinterpret_cast<float*>(smem_raw);                 // [V] processed logits
   uint32_t* s_key = reinterpret_cast<uint32_t*>(s_x + p.V);        // [1024] sort path only
@@ -74,8 +76,8 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) k_sample(const SampleP p) {
   const int tid = threadIdx.x;
   const int row = blockIdx.x, V = p.V, rpi = p.rows_per_item;
   const int item = row / rpi, qi = row % rpi;
-  const int n_gen = p.st ? p.st->n_gen : p.n_gen_fixed;
-  const int step = p.st ? p.st->step : p.step_fixed;
+  const int n_gen = p.st ? ldg_cg(&p.st->n_gen) : p.n_gen_fixed;
+  const int step = p.st ? ldg_cg(&p.st->step) : p.step_fixed;
   const ctb_sampler_config& c = p.cfg;
   const float* lg = p.logits + (size_t)row * V;
 
@@ -84,13 +86,13 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) k_sample(const SampleP p) {
   const bool pen = c.penalty_on && row < c.penalty_max_ids;
   if (pen) {
     nwin = min(n_gen, c.past_window);
-    if (tid < nwin) s_win[tid] = p.gen_ids[((size_t)item * p.gen_stride + (n_gen - nwin + tid)) * p.gen_inner + qi];
+    if (tid < nwin) s_win[tid] = ldg_cg(&p.gen_ids[((size_t)item * p.gen_stride + (n_gen - nwin + tid)) * p.gen_inner + qi]);
   }
   __syncthreads();
   // ---- S1 temperature, S2 penalty
   const float temp = c.temperature[qi];
   for (int v = tid; v < V; v += SAMPLE_THREADS) {
-    float x = __fdiv_rn(lg[v], temp);
+    float x = __fdiv_rn(ldg_cg(&lg[v]), temp);
     if (pen) {
       int cnt = 0;
       for (int w = 0; w < nwin; ++w) cnt += (s_win[w] == v);
@@ -257,33 +259,36 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) k_sample(const SampleP p) {
 
 // finish / write-back / counters (gpt.py:512-525,572-577).  One CTA, one thread per batch row.
 __global__ void k_finalize(const FinalP p) {
-  if (p.st->all_finished) return;
+  pdl_trigger();
+  pdl_wait();
+  if (ldg_cg(&p.st->all_finished)) return;
   __shared__ int s_any, s_notall;
   if (threadIdx.x == 0) { s_any = 0; s_notall = 0; }
   __syncthreads();
-  const int n = p.st->n_gen;
+  const int n = ldg_cg(&p.st->n_gen);
+  const int step0 = ldg_cg(&p.st->step);
   for (int b = threadIdx.x; b < p.B; b += blockDim.x) {
     bool eos = false;
-    for (int q = 0; q < p.rows_per_item; ++q) eos |= (p.idx[b * p.rows_per_item + q] == p.eos);
-    const bool fin = p.finish[b] || eos;
+    for (int q = 0; q < p.rows_per_item; ++q) eos |= (ldg_cg(&p.idx[b * p.rows_per_item + q]) == p.eos);
+    const bool fin = ldg_cg(&p.finish[b]) || eos;
     p.finish[b] = fin ? 1 : 0;
     int32_t* dst = p.ids_out + ((size_t)b * p.max_new + n) * p.num_vq;
-    for (int q = 0; q < p.num_vq; ++q) dst[q] = p.idx[b * p.rows_per_item + (p.rows_per_item == 1 ? 0 : q)];
+    for (int q = 0; q < p.num_vq; ++q) dst[q] = ldg_cg(&p.idx[b * p.rows_per_item + (p.rows_per_item == 1 ? 0 : q)]);
     if (fin) atomicOr(&s_any, 1); else { atomicOr(&s_notall, 1); }
     // gpt.py:527: at i == 0 with any finished row the reference returns before end_idx moves
     (void)0;
   }
   __syncthreads();
-  const bool first_abort = (p.st->step == 0) && s_any;
+  const bool first_abort = (step0 == 0) && s_any;
   if (!first_abort)
     for (int b = threadIdx.x; b < p.B; b += blockDim.x)
-      if (!p.finish[b]) p.end_idx[b] += 1;
+      if (!p.finish[b]) p.end_idx[b] = ldg_cg(&p.end_idx[b]) + 1;
   __syncthreads();
   if (threadIdx.x == 0) {
     if (first_abort) { p.st->any_first = 1; p.st->all_finished = 1; }
     else if (!s_notall) p.st->all_finished = 1;
     p.st->n_gen = n + 1;
-    p.st->step = p.st->step + 1;
+    p.st->step = step0 + 1;
   }
 }
 
