@@ -1,7 +1,11 @@
 // extern "C" entry points for hot path 2 (token -> waveform); see include/chattts_b200.h.
-#include "decoder_kernels.cuh"
+#include <cudaTypedefs.h>
+
+#include "tc_gemm.cuh"
 
 using namespace ctb;
+
+__global__ void k_split_tf32(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo, int64_t n);
 
 namespace {
 
@@ -50,7 +54,7 @@ DvaeOff dvae_layout(const ctb_convstack_config& c) {
   return o;
 }
 
-int spec_k(const ctb_vocos_config& c) { return ((c.n_fft + 2) + 15) / 16 * 16; }  // 1026 -> 1040
+int spec_k(const ctb_vocos_config& c) { return ((c.n_fft + 2) + 31) / 32 * 32; }  // 1026 -> 1056
 
 VocosOff vocos_layout(const ctb_vocos_config& c) {
   VocosOff o{};
@@ -80,6 +84,9 @@ struct ctb_decoder {
   int max_batch, max_tokens;
   size_t max_rows;  // max_batch * 2 * max_tokens frames
   float *bufA, *bufB, *bufH, *mel_tm, *staged_in;
+  // tcgen05 path: tf32-rounded hi / lo copies of both blobs (same offsets as the fp32 blobs)
+  float *dW_hi, *dW_lo, *vW_hi, *vW_lo;
+  bool use_tc;
 };
 
 extern "C" int64_t ctb_dvae_blob_floats(const ctb_convstack_config* c) { return c ? dvae_layout(*c).total : -1; }
@@ -87,7 +94,7 @@ extern "C" int64_t ctb_vocos_blob_floats(const ctb_vocos_config* c) { return c ?
 
 extern "C" int ctb_decoder_destroy(ctb_decoder* h) {
   if (!h) return CTB_OK;
-  void* ptrs[] = {h->bufA, h->bufB, h->bufH, h->mel_tm, h->staged_in};
+  void* ptrs[] = {h->bufA, h->bufB, h->bufH, h->mel_tm, h->staged_in, h->dW_hi, h->dW_lo, h->vW_hi, h->vW_lo};
   for (void* p : ptrs) if (p) cudaFree(p);
   delete h;
   return CTB_OK;
@@ -125,19 +132,92 @@ extern "C" int ctb_decoder_create(const ctb_convstack_config* dc, const float* d
   A(&h->bufH, R * wide);
   A(&h->mel_tm, R * MEL_PAD);
   A(&h->staged_in, R * dc->idim);
+  h->use_tc = getenv("CTB_DECODER_FMA") == nullptr;
+  if (h->use_tc) {
+    if (h->dW) { A(&h->dW_hi, h->dl.total); A(&h->dW_lo, h->dl.total); }
+    if (h->vW) { A(&h->vW_hi, h->vl.total); A(&h->vW_lo, h->vl.total); }
+  }
   if (e != cudaSuccess) {
     ctb_decoder_destroy(h);
     return set_err(CTB_ERR_NOMEM, "decoder buffers: %s", cudaGetErrorString(e));
+  }
+  if (h->use_tc) {
+    if (h->dW) k_split_tf32<<<1024, 256>>>(h->dW, h->dW_hi, h->dW_lo, h->dl.total);
+    if (h->vW) k_split_tf32<<<1024, 256>>>(h->vW, h->vW_hi, h->vW_lo, h->vl.total);
+    CTB_CUDA(cudaDeviceSynchronize());
+    CTB_CUDA(cudaFuncSetAttribute(k_tc_gemm<GE_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    CTB_CUDA(cudaFuncSetAttribute(k_tc_gemm<GE_BIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    CTB_CUDA(cudaFuncSetAttribute(k_tc_gemm<GE_GELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    CTB_CUDA(cudaFuncSetAttribute(k_tc_gemm<GE_SCALE_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    CTB_CUDA(cudaFuncSetAttribute(k_tc_gemm<GE_COEF>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    CTB_CUDA(cudaFuncSetAttribute(k_tc_gemm<GE_SPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
   }
   *out = h;
   return CTB_OK;
 }
 
 // ------------------------------------------------------------------ launch helpers
+__global__ void k_split_tf32(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float x = w[i], h = to_tf32(x);
+    hi[i] = h;
+    lo[i] = to_tf32(x - h);
+  }
+}
+
+static PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }
+  return fn;
+}
+
+static int make_map(CUtensorMap* m, const float* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                    const cuuint32_t* box) {
+  auto enc = tensor_map_encoder();
+  if (!enc) return set_err(CTB_ERR_CUDA, "cuTensorMapEncodeTiled unavailable");
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<float*>(base), dims, strides_bytes, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_err(CTB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return CTB_OK;
+}
+
+struct GemmCtx {  // which blob a weight pointer lives in, for the hi / lo lookup of the tensor-core path
+  const float* W; const float* hi; const float* lo; bool tc;
+};
+
 template <int EPI>
-static int gemm(cudaStream_t s, const float* A, int lda, int M, int N, int K, int taps, int Cin, int dil, int pad,
-                int F, const float* W, const float* bias, const float* gamma, const float* res, int ldres, float* C,
-                int ldc) {
+static int gemm(cudaStream_t s, const GemmCtx& gc, const float* A, int lda, int M, int N, int K, int taps, int Cin,
+                int dil, int pad, int F, const float* W, const float* bias, const float* gamma, const float* res,
+                int ldres, float* C, int ldc) {
+  if (gc.tc && K % TC_BK == 0 && Cin % TC_BK == 0 && M % F == 0) {
+    const int B = M / F;
+    CUtensorMap ma, mh, ml;
+    const cuuint64_t adims[3] = {(cuuint64_t)lda, (cuuint64_t)F, (cuuint64_t)B};
+    const cuuint64_t astr[2] = {(cuuint64_t)lda * 4, (cuuint64_t)F * lda * 4};
+    const cuuint32_t abox[3] = {TC_BK, TC_BM, 1};
+    const cuuint64_t wdims[2] = {(cuuint64_t)K, (cuuint64_t)N};
+    const cuuint64_t wstr[1] = {(cuuint64_t)K * 4};
+    const cuuint32_t wbox[2] = {TC_BK, TC_BN};
+    int rc;
+    if ((rc = make_map(&ma, A, 3, adims, astr, abox))) return rc;
+    if ((rc = make_map(&mh, gc.hi + (W - gc.W), 2, wdims, wstr, wbox))) return rc;
+    if ((rc = make_map(&ml, gc.lo + (W - gc.W), 2, wdims, wstr, wbox))) return rc;
+    TcGemmP p{};
+    p.N = N; p.K = K; p.taps = taps; p.Cin = Cin; p.dil = dil; p.pad = pad; p.F = F; p.B = B;
+    p.bias = bias; p.gamma = gamma; p.res = res; p.ldres = ldres; p.C = C; p.ldc = ldc;
+    dim3 grid((N + TC_BN - 1) / TC_BN, B * ((F + TC_BM - 1) / TC_BM));
+    k_tc_gemm<EPI><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(ma, mh, ml, p);
+    CTB_LAUNCH_CHECK();
+    return CTB_OK;
+  }
   GemmP p{};
   p.A = A; p.lda = lda; p.M = M; p.N = N; p.K = K; p.taps = taps; p.Cin = Cin; p.dil = dil; p.pad = pad; p.F = F;
   p.W = W; p.bias = bias; p.gamma = gamma; p.res = res; p.ldres = ldres; p.C = C; p.ldc = ldc;
@@ -162,13 +242,13 @@ static int dwln(cudaStream_t s, const float* x, float* out, int M, int F, int C,
 }
 
 // x (time-major [M, C]) -> x through one ConvNeXt block; tmp = [M, C], hbuf = [M, inter]
-static int convnext(cudaStream_t s, const float* W, const BlockOff& b, float* x, float* tmp, float* hbuf, int M,
+static int convnext(cudaStream_t s, const GemmCtx& gc, const float* W, const BlockOff& b, float* x, float* tmp, float* hbuf, int M,
                     int F, int C, int inter, int dil) {
   int rc;
   if ((rc = dwln(s, x, tmp, M, F, C, 7, dil, W + b.dw_w, W + b.dw_b, W + b.ln_w, W + b.ln_b))) return rc;
-  if ((rc = gemm<GE_GELU>(s, tmp, C, M, inter, C, 1, C, 1, 0, F, W + b.pw1_w, W + b.pw1_b, nullptr, nullptr, 0, hbuf,
+  if ((rc = gemm<GE_GELU>(s, gc, tmp, C, M, inter, C, 1, C, 1, 0, F, W + b.pw1_w, W + b.pw1_b, nullptr, nullptr, 0, hbuf,
                           inter))) return rc;
-  return gemm<GE_SCALE_RES>(s, hbuf, inter, M, C, inter, 1, inter, 1, 0, F, W + b.pw2_w, W + b.pw2_b, W + b.gamma, x,
+  return gemm<GE_SCALE_RES>(s, gc, hbuf, inter, M, C, inter, 1, inter, 1, 0, F, W + b.pw2_w, W + b.pw2_b, W + b.gamma, x,
                             C, x, C);
 }
 
@@ -179,6 +259,7 @@ static int dvae_run(ctb_decoder* h, const void* in, int layout, int B, int T, fl
   const DvaeOff& L = h->dl;
   const float* W = h->dW;
   const int F = 2 * T, M = B * F;
+  const GemmCtx gc{h->dW, h->dW_hi, h->dW_lo, h->use_tc};
   int rc;
   const float* x0;
   if (layout == 1) {
@@ -201,16 +282,16 @@ static int dvae_run(ctb_decoder* h, const void* in, int layout, int B, int T, fl
     x0 = h->staged_in;
   }
   // conv_in: Conv1d(idim -> bn, k3, p1) + GELU + Conv1d(bn -> hidden, k3, p1)   (dvae.py:144-148)
-  if ((rc = gemm<GE_GELU>(s, x0, c.idim, M, c.bn_dim, 3 * c.idim, 3, c.idim, 1, 1, F, W + L.in0_w, W + L.in0_b,
+  if ((rc = gemm<GE_GELU>(s, gc, x0, c.idim, M, c.bn_dim, 3 * c.idim, 3, c.idim, 1, 1, F, W + L.in0_w, W + L.in0_b,
                           nullptr, nullptr, 0, h->bufB, c.bn_dim))) return rc;
-  if ((rc = gemm<GE_BIAS>(s, h->bufB, c.bn_dim, M, c.hidden, 3 * c.bn_dim, 3, c.bn_dim, 1, 1, F, W + L.in2_w,
+  if ((rc = gemm<GE_BIAS>(s, gc, h->bufB, c.bn_dim, M, c.hidden, 3 * c.bn_dim, 3, c.bn_dim, 1, 1, F, W + L.in2_w,
                           W + L.in2_b, nullptr, nullptr, 0, h->bufA, c.hidden))) return rc;
   for (int i = 0; i < c.n_layer; ++i)
-    if ((rc = convnext(s, W, L.blk[i], h->bufA, h->bufB, h->bufH, M, F, c.hidden, 4 * c.hidden, c.dilation))) return rc;
+    if ((rc = convnext(s, gc, W, L.blk[i], h->bufA, h->bufB, h->bufH, M, F, c.hidden, 4 * c.hidden, c.dilation))) return rc;
   // conv_out 1x1 (no bias), out_conv k3 (no bias) * coef        (dvae.py:159,236,289-297)
-  if ((rc = gemm<GE_NONE>(s, h->bufA, c.hidden, M, c.odim, c.hidden, 1, c.hidden, 1, 0, F, W + L.conv_out_w, nullptr,
+  if ((rc = gemm<GE_NONE>(s, gc, h->bufA, c.hidden, M, c.odim, c.hidden, 1, c.hidden, 1, 0, F, W + L.conv_out_w, nullptr,
                           nullptr, nullptr, 0, h->bufB, c.odim))) return rc;
-  if ((rc = gemm<GE_COEF>(s, h->bufB, c.out_dim, M, MEL_PAD, 3 * c.out_dim, 3, c.out_dim, 1, 1, F, W + L.out_conv_w,
+  if ((rc = gemm<GE_COEF>(s, gc, h->bufB, c.out_dim, M, MEL_PAD, 3 * c.out_dim, 3, c.out_dim, 1, 1, F, W + L.out_conv_w,
                           nullptr, W + L.coef, nullptr, 0, h->mel_tm, MEL_PAD))) return rc;
   if (mel_cf) {
     dim3 g((F + 31) / 32, (MEL + 31) / 32, B);
@@ -225,6 +306,7 @@ static int vocos_run(ctb_decoder* h, const float* mel_cf, int B, int F, float* w
   const VocosOff& L = h->vl;
   const float* W = h->vW;
   const int M = B * F, SK = spec_k(c);
+  const GemmCtx gc{h->vW, h->vW_hi, h->vW_lo, h->use_tc};
   int rc;
   if (mel_cf) {
     dim3 g((F + 31) / 32, (MEL_PAD + 31) / 32, B);
@@ -232,17 +314,17 @@ static int vocos_run(ctb_decoder* h, const float* mel_cf, int B, int F, float* w
     CTB_LAUNCH_CHECK();
   }
   // backbone: Conv1d(100 -> dim, k7, p3) -> LN -> ConvNeXt x num_layers -> LN
-  if ((rc = gemm<GE_BIAS>(s, h->mel_tm, MEL_PAD, M, c.dim, 7 * MEL_PAD, 7, MEL_PAD, 1, 3, F, W + L.embed_w,
+  if ((rc = gemm<GE_BIAS>(s, gc, h->mel_tm, MEL_PAD, M, c.dim, 7 * MEL_PAD, 7, MEL_PAD, 1, 3, F, W + L.embed_w,
                           W + L.embed_b, nullptr, nullptr, 0, h->bufB, c.dim))) return rc;
   if ((rc = dwln(s, h->bufB, h->bufA, M, F, c.dim, 0, 1, nullptr, nullptr, W + L.norm_w, W + L.norm_b))) return rc;
   for (int i = 0; i < c.num_layers; ++i)
-    if ((rc = convnext(s, W, L.blk[i], h->bufA, h->bufB, h->bufH, M, F, c.dim, c.intermediate_dim, 1))) return rc;
+    if ((rc = convnext(s, gc, W, L.blk[i], h->bufA, h->bufB, h->bufH, M, F, c.dim, c.intermediate_dim, 1))) return rc;
   if ((rc = dwln(s, h->bufA, h->bufB, M, F, c.dim, 0, 1, nullptr, nullptr, W + L.fin_w, W + L.fin_b))) return rc;
   // ISTFTHead: Linear(dim -> n_fft + 2) -> (mag, phase) -> complex spectrum (interleaved re/im)
-  if ((rc = gemm<GE_SPEC>(s, h->bufB, c.dim, M, SK, c.dim, 1, c.dim, 1, 0, F, W + L.head_w, W + L.head_b, nullptr,
+  if ((rc = gemm<GE_SPEC>(s, gc, h->bufB, c.dim, M, SK, c.dim, 1, c.dim, 1, 0, F, W + L.head_w, W + L.head_b, nullptr,
                           nullptr, 0, h->bufA, SK))) return rc;
   // inverse real DFT * window as a GEMM against the constant basis, then overlap-add / envelope
-  if ((rc = gemm<GE_NONE>(s, h->bufA, SK, M, c.n_fft, SK, 1, SK, 1, 0, F, W + L.basis, nullptr, nullptr, nullptr, 0,
+  if ((rc = gemm<GE_NONE>(s, gc, h->bufA, SK, M, c.n_fft, SK, 1, SK, 1, 0, F, W + L.basis, nullptr, nullptr, nullptr, 0,
                           h->bufH, c.n_fft))) return rc;
   const size_t total = (size_t)B * c.hop_length * (F - 1);
   k_overlap_add<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(h->bufH, W + L.window, wav, B, F, c.n_fft, c.hop_length);

@@ -19,6 +19,8 @@ int set_err(int code, const char* fmt, ...) {
   return code;
 }
 
+int g_num_sms = 148;
+
 static int bt_for(int B) {
   int bt = 1;
   while (bt < B && bt < 32) bt <<= 1;
@@ -28,6 +30,7 @@ static int bt_for(int B) {
 }  // namespace ctb
 
 using namespace ctb;
+using ctb::g_num_sms;
 
 struct ctb_gpt {
   ctb_gpt_config cfg;
@@ -102,6 +105,12 @@ extern "C" int ctb_gpt_create(const ctb_gpt_config* c, const float* weights_dev,
   int dev_count = 0;
   CTB_CUDA(cudaGetDeviceCount(&dev_count));
   if (dev_count < 1) return set_err(CTB_ERR_CUDA, "no CUDA device: chattts_b200 has no CPU path");
+  {
+    int dev = 0, sms = 0;
+    CTB_CUDA(cudaGetDevice(&dev));
+    CTB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    g_num_sms = sms;
+  }
   ctb_gpt* h = new ctb_gpt();
   memset(h, 0, sizeof(*h));
   h->cfg = *c;
@@ -163,8 +172,18 @@ static int launch_gemv_t(const GemvP& p, int ntiles, cudaStream_t s) {
     CTB_CUDA(cudaFuncSetAttribute(k_gemv<BT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
-  dim3 grid((p.ntasks + GEMV_WARPS - 1) / GEMV_WARPS, ntiles);
-  CTB_CUDA(launch_pdl(k_gemv<BT, EPI>, grid, dim3(GEMV_WARPS * 32), smem, s, p));
+  // persistent: one CTA per SM strides over the warp tasks (DOWN: clusters of DOWN_SPLIT CTAs)
+  int ctas = std::min(g_num_sms, (p.ntasks + GEMV_WARPS - 1) / GEMV_WARPS);
+  unsigned cluster = 1;
+  if (EPI == EPI_DOWN) {
+    cluster = DOWN_SPLIT;
+    const int groups = std::max(1, std::min(g_num_sms / DOWN_SPLIT, (p.ntasks + GEMV_WARPS - 1) / GEMV_WARPS));
+    if ((p.ntasks + groups * GEMV_WARPS - 1) / (groups * GEMV_WARPS) > DOWN_MAX_TASKS)
+      return set_err(CTB_ERR_STATE, "DOWN kernel: too few SMs (%d) for %d tasks", g_num_sms, p.ntasks);
+    ctas = groups * DOWN_SPLIT;
+  }
+  dim3 grid(ctas, ntiles);
+  CTB_CUDA(launch_pdl_cluster(k_gemv<BT, EPI>, grid, dim3(GEMV_WARPS * 32), smem, s, cluster, p));
   CTB_LAUNCH_CHECK();
   return CTB_OK;
 }

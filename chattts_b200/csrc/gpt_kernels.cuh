@@ -60,164 +60,223 @@ __device__ __forceinline__ size_t kv_off(int page, int which, int h, int slot, i
   return ((((size_t)page * 2 + which) * Hkv + h) * kPageTokens + slot) * hd;
 }
 
+// ---- cluster / async-copy helpers (sm_90+)
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float ld_dsmem(const float* local_smem_ptr, uint32_t rank) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(local_smem_ptr);
+  uint32_t r; float v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(rank));
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(r) : "memory");
+  return v;
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+constexpr int DOWN_SPLIT = 4;       // K = 3072 split over a 4-CTA cluster, partials merged through DSMEM
+constexpr int DOWN_MAX_TASKS = 4;   // row-pair tasks per warp in the DOWN kernel (ceil(384 / (groups*8)) <= 4 for >= 12 groups)
+
+// Persistent weight-streaming GEMV / skinny GEMM:  y[b, r] = sum_k W[r, k] * x[b, k]  for a batch tile of
+// BT rows.  grid.x CTAs (one per SM) stride over 2-row warp tasks; the batch tile's activations are staged
+// ONCE per CTA in shared memory with cp.async (L2-coherent), the RMSNorm prologue runs on that copy, and each
+// warp streams its rows' weights with 128-bit non-allocating loads, next task prefetched under the FMAs.
+// EPI_DOWN: launched as clusters of DOWN_SPLIT CTAs; rank r owns K-chunk r of the same rows, the partial sums
+// meet in rank 0 through distributed shared memory in a fixed order (deterministic, no atomics).
 template <int BT, int EPI>
 __global__ void __launch_bounds__(GEMV_WARPS * 32) k_gemv(const GemvP p) {
   pdl_trigger();
   extern __shared__ __align__(16) float xs[];  // [BT][KC]
   __shared__ float rinv[BT];
+  __shared__ float red[(EPI == EPI_DOWN) ? GEMV_WARPS * DOWN_MAX_TASKS * 2 * BT : 1];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int task = blockIdx.x * GEMV_WARPS + warp;
-  const bool has_task = task < p.ntasks;
   const int bbase = blockIdx.y * BT;        // batch tile (B > 32 re-streams the weights per tile)
   const int nb = min(BT, p.B - bbase);      // live rows in this tile
+  const int kc = (EPI == EPI_DOWN) ? (int)cluster_ctarank() : 0;
+  const int cta = (EPI == EPI_DOWN) ? blockIdx.x / DOWN_SPLIT : blockIdx.x;
+  const int ncta = (EPI == EPI_DOWN) ? gridDim.x / DOWN_SPLIT : gridDim.x;
+  const int tstride = ncta * GEMV_WARPS;
+  const int task0 = cta * GEMV_WARPS + warp;
 
-  // ---- rows of this warp's task
-  int r0 = 0, r1 = 0;
-  if (EPI == EPI_QKV) {
-    // task -> (which, head, j): rows j and j+32 of one head so RoPE pairs stay in-warp
-    const int half = p.hd / 2;
-    int t = task, base = 0, which = 0;
-    const int nq = p.Hq * half, nk = p.Hkv * half;
-    if (t >= nq + nk) { which = 2; t -= nq + nk; base = (p.Hq + p.Hkv) * p.hd; }
-    else if (t >= nq) { which = 1; t -= nq; base = p.Hq * p.hd; }
-    (void)which;
-    r0 = base + (t / half) * p.hd + (t % half);
-    r1 = r0 + half;
-  } else if (EPI == EPI_GATEUP) {
-    r0 = task; r1 = p.I + task;
-  } else {
-    r0 = 2 * task; r1 = 2 * task + 1;
-  }
-  const bool r1_valid = r1 < p.nrows;
-  if (!r1_valid) r1 = r0;
-
-  float acc0[BT], acc1[BT];
-#pragma unroll
-  for (int b = 0; b < BT; ++b) { acc0[b] = 0.f; acc1[b] = 0.f; }
-
-  const int nchunks = p.K / KC;
-  const float4* w0p = reinterpret_cast<const float4*>(p.W + (size_t)r0 * p.K) + lane;
-  const float4* w1p = reinterpret_cast<const float4*>(p.W + (size_t)r1 * p.K) + lane;
-
-  // issue the first chunk's weight loads before touching activations: they do not depend on
-  // the previous kernel and hide the prologue latency
-  float4 w0[6], w1[6];
-  if (has_task) {
+  auto task_rows = [&](int task, int& r0, int& r1) {
+    if (EPI == EPI_QKV) {
+      // task -> (q|k|v, head, j): rows j and j + hd/2 of one head so RoPE pairs stay in-warp
+      const int half = p.hd / 2;
+      int t = task, base = 0;
+      const int nq = p.Hq * half, nk = p.Hkv * half;
+      if (t >= nq + nk) { t -= nq + nk; base = (p.Hq + p.Hkv) * p.hd; }
+      else if (t >= nq) { t -= nq; base = p.Hq * p.hd; }
+      r0 = base + (t / half) * p.hd + (t % half);
+      r1 = r0 + half;
+    } else if (EPI == EPI_GATEUP) {
+      r0 = task; r1 = p.I + task;
+    } else {
+      r0 = 2 * task; r1 = min(2 * task + 1, p.nrows - 1);
+    }
+  };
+  auto load_w = [&](int task, float4 (&w0)[6], float4 (&w1)[6]) {
+    int r0, r1;
+    task_rows(task, r0, r1);
+    const float4* w0p = reinterpret_cast<const float4*>(p.W + (size_t)r0 * p.K + kc * KC) + lane;
+    const float4* w1p = reinterpret_cast<const float4*>(p.W + (size_t)r1 * p.K + kc * KC) + lane;
 #pragma unroll
     for (int i = 0; i < 6; ++i) { w0[i] = ldg_stream(w0p + i * 32); w1[i] = ldg_stream(w1p + i * 32); }
-  }
-  pdl_wait();  // everything below reads activations / loop state written by earlier kernels
-  if (p.check_finished && ldg_cg(&p.st->all_finished)) return;
+  };
 
-  for (int c = 0; c < nchunks; ++c) {
-    if (c > 0) __syncthreads();
-    // ---- stage activations [BT][KC] (zero rows beyond B)
-    for (int i = tid; i < BT * (KC / 4); i += GEMV_WARPS * 32) {
-      const int b = i / (KC / 4), k4 = i % (KC / 4);
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (b < nb) v = ldg_cg(reinterpret_cast<const float4*>(p.xin + (size_t)(bbase + b) * p.K + c * KC + k4 * 4));
-      reinterpret_cast<float4*>(xs)[i] = v;
+  // the first task's weights do not depend on earlier kernels: request them before the PDL wait
+  float4 w0[6], w1[6];
+  if (task0 < p.ntasks) load_w(task0, w0, w1);
+  pdl_wait();  // everything below reads activations / loop state written by earlier kernels
+  if (p.check_finished && ldg_cg(&p.st->all_finished)) {
+    if (EPI == EPI_DOWN) { cluster_sync_all(); cluster_sync_all(); }
+    return;
+  }
+
+  // ---- stage the batch tile's activations (K chunk kc) once per CTA
+  for (int i = tid; i < BT * (KC / 4); i += GEMV_WARPS * 32) {
+    const int b = i / (KC / 4), k4 = i % (KC / 4);
+    if (b < nb) cp_async16(&xs[i * 4], p.xin + (size_t)(bbase + b) * p.K + kc * KC + k4 * 4);
+    else reinterpret_cast<float4*>(xs)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  cp_async_wait_all();
+  __syncthreads();
+  if (p.normw != nullptr) {
+    // RMSNorm prologue (K == KC): HF LlamaRMSNorm  w * (x * rsqrt(mean(x^2) + eps))
+    for (int b = warp; b < BT; b += GEMV_WARPS) {
+      float ss = 0.f;
+#pragma unroll
+      for (int k = lane; k < KC; k += 32) { const float v = xs[b * KC + k]; ss = fmaf(v, v, ss); }
+      ss = warp_sum(ss);
+      if (lane == 0) rinv[b] = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(__fdiv_rn(ss, (float)KC), p.eps)));
     }
     __syncthreads();
-    if (p.normw != nullptr) {
-      // RMSNorm prologue (K == KC): HF LlamaRMSNorm  w * (x * rsqrt(mean(x^2) + eps))
-      for (int b = warp; b < BT; b += GEMV_WARPS) {
-        float ss = 0.f;
-        for (int k = lane; k < KC; k += 32) { float v = xs[b * KC + k]; ss = fmaf(v, v, ss); }
-        ss = warp_sum(ss);
-        if (lane == 0) rinv[b] = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(__fdiv_rn(ss, (float)KC), p.eps)));
-      }
-      __syncthreads();
-      for (int i = tid; i < BT * KC; i += GEMV_WARPS * 32) {
-        const int b = i / KC, k = i % KC;
-        xs[i] = __fmul_rn(p.normw[k], __fmul_rn(xs[i], rinv[b]));
-      }
-      __syncthreads();
-      if (EPI == EPI_HEADS && p.hidden_out != nullptr && blockIdx.x == 0) {
-        // last_hidden_state of this step (gpt.py:430-436), written once
-        const int step = ldg_cg(&p.st->n_gen);
-        for (int i = tid; i < nb * KC; i += GEMV_WARPS * 32) {
-          const int b = i / KC, k = i % KC;
-          p.hidden_out[(size_t)(bbase + b) * p.hidden_stride + (size_t)step * KC + k] = xs[i];
-        }
-      }
+    for (int i = tid; i < BT * KC; i += GEMV_WARPS * 32) {
+      const int b = i / KC, k = i % KC;
+      xs[i] = __fmul_rn(__ldg(p.normw + k), __fmul_rn(xs[i], rinv[b]));
     }
-    if (has_task) {
-      float4 n0[6], n1[6];
-      const bool more = (c + 1) < nchunks;
-      if (more) {
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-          n0[i] = ldg_stream(w0p + (c + 1) * (KC / 4) + i * 32);
-          n1[i] = ldg_stream(w1p + (c + 1) * (KC / 4) + i * 32);
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < 6; ++i) {
-#pragma unroll
-        for (int b = 0; b < BT; ++b) {
-          const float4 xv = reinterpret_cast<const float4*>(xs)[b * (KC / 4) + i * 32 + lane];
-          acc0[b] = fmaf(w0[i].x, xv.x, acc0[b]); acc0[b] = fmaf(w0[i].y, xv.y, acc0[b]);
-          acc0[b] = fmaf(w0[i].z, xv.z, acc0[b]); acc0[b] = fmaf(w0[i].w, xv.w, acc0[b]);
-          acc1[b] = fmaf(w1[i].x, xv.x, acc1[b]); acc1[b] = fmaf(w1[i].y, xv.y, acc1[b]);
-          acc1[b] = fmaf(w1[i].z, xv.z, acc1[b]); acc1[b] = fmaf(w1[i].w, xv.w, acc1[b]);
-        }
-      }
-      if (more) {
-#pragma unroll
-        for (int i = 0; i < 6; ++i) { w0[i] = n0[i]; w1[i] = n1[i]; }
+    __syncthreads();
+    if (EPI == EPI_HEADS && p.hidden_out != nullptr && blockIdx.x == 0) {
+      // last_hidden_state of this step (gpt.py:430-436), written once per batch tile
+      const int step = ldg_cg(&p.st->n_gen);
+      for (int i = tid; i < nb * KC; i += GEMV_WARPS * 32) {
+        const int b = i / KC, k = i % KC;
+        p.hidden_out[(size_t)(bbase + b) * p.hidden_stride + (size_t)step * KC + k] = xs[i];
       }
     }
   }
-  if (!has_task) return;
 
-  warp_reduce_scatter<BT>(acc0);
-  warp_reduce_scatter<BT>(acc1);
-  constexpr int LPB = 32 / BT;  // lanes per batch row after the scatter
-  if ((lane % LPB) != 0 || (lane / LPB) >= nb) return;
-  const int b = bbase + lane / LPB;
-  const float v0 = acc0[0], v1 = acc1[0];
+  constexpr int LPB = 32 / BT;  // lanes per batch row after the reduce-scatter
+  int jtask = 0;
+  for (int task = task0; task < p.ntasks; task += tstride, ++jtask) {
+    float4 n0[6], n1[6];
+    const bool more = task + tstride < p.ntasks;
+    if (more) load_w(task + tstride, n0, n1);
+    float acc0[BT], acc1[BT];
+#pragma unroll
+    for (int b = 0; b < BT; ++b) { acc0[b] = 0.f; acc1[b] = 0.f; }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+#pragma unroll
+      for (int b = 0; b < BT; ++b) {
+        const float4 xv = reinterpret_cast<const float4*>(xs)[b * (KC / 4) + i * 32 + lane];
+        acc0[b] = fmaf(w0[i].x, xv.x, acc0[b]); acc0[b] = fmaf(w0[i].y, xv.y, acc0[b]);
+        acc0[b] = fmaf(w0[i].z, xv.z, acc0[b]); acc0[b] = fmaf(w0[i].w, xv.w, acc0[b]);
+        acc1[b] = fmaf(w1[i].x, xv.x, acc1[b]); acc1[b] = fmaf(w1[i].y, xv.y, acc1[b]);
+        acc1[b] = fmaf(w1[i].z, xv.z, acc1[b]); acc1[b] = fmaf(w1[i].w, xv.w, acc1[b]);
+      }
+    }
+    if (more) {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) { w0[i] = n0[i]; w1[i] = n1[i]; }
+    }
+    warp_reduce_scatter<BT>(acc0);
+    warp_reduce_scatter<BT>(acc1);
+    const bool writer = (lane % LPB) == 0 && (lane / LPB) < nb;
+    const int b = bbase + lane / LPB;
+    const float v0 = acc0[0], v1 = acc1[0];
+    int r0, r1;
+    task_rows(task, r0, r1);
+    const bool r1_valid = (EPI == EPI_QKV || EPI == EPI_GATEUP) ? true : (2 * task + 1 < p.nrows);
 
-  if (EPI == EPI_QKV) {
-    if (!ldg_cg(&p.active[b])) return;
-    const int half = p.hd / 2;
-    const int nq = p.Hq * half, nk = p.Hkv * half;
-    int t = task, which = 0;
-    if (t >= nq + nk) { which = 2; t -= nq + nk; }
-    else if (t >= nq) { which = 1; t -= nq; }
-    const int h = t / half, j = t % half;
-    const int pos = ldg_cg(&p.pos[b]);
-    float o0 = v0, o1 = v1;
-    if (which < 2) {
-      // HF apply_rotary_pos_emb: q*cos + rotate_half(q)*sin, each product rounded separately
-      const float c0 = p.rope_cos[(size_t)pos * p.hd + j], s0 = p.rope_sin[(size_t)pos * p.hd + j];
-      const float c1 = p.rope_cos[(size_t)pos * p.hd + j + half], s1 = p.rope_sin[(size_t)pos * p.hd + j + half];
-      o0 = __fadd_rn(__fmul_rn(v0, c0), __fmul_rn(-v1, s0));
-      o1 = __fadd_rn(__fmul_rn(v1, c1), __fmul_rn(v0, s1));
+    if (EPI == EPI_DOWN) {
+      // partial over K chunk kc -> this CTA's smem; merged by cluster rank 0 below
+      if ((lane % LPB) == 0 && jtask < DOWN_MAX_TASKS) {
+        float* r = red + ((warp * DOWN_MAX_TASKS + jtask) * 2) * BT + lane / LPB;
+        r[0] = v0; r[BT] = v1;
+      }
+      continue;
     }
-    if (which == 0) {
-      p.out[(size_t)b * p.Hq * p.hd + h * p.hd + j] = o0;
-      p.out[(size_t)b * p.Hq * p.hd + h * p.hd + j + half] = o1;
-    } else {
-      const int page = p.block_table[b * p.pages_per_row + pos / kPageTokens];
-      float* dst = p.kv + kv_off(page, which - 1, h, pos % kPageTokens, p.Hkv, p.hd);
-      dst[j] = o0; dst[j + half] = o1;
+    if (!writer) continue;
+    if (EPI == EPI_QKV) {
+      if (!ldg_cg(&p.active[b])) continue;
+      const int half = p.hd / 2;
+      const int nq = p.Hq * half, nk = p.Hkv * half;
+      int t = task, which = 0;
+      if (t >= nq + nk) { which = 2; t -= nq + nk; }
+      else if (t >= nq) { which = 1; t -= nq; }
+      const int h = t / half, j = t % half;
+      const int pos = ldg_cg(&p.pos[b]);
+      float o0 = v0, o1 = v1;
+      if (which < 2) {
+        // HF apply_rotary_pos_emb: q*cos + rotate_half(q)*sin, each product rounded separately
+        const float c0 = __ldg(p.rope_cos + (size_t)pos * p.hd + j), s0 = __ldg(p.rope_sin + (size_t)pos * p.hd + j);
+        const float c1 = __ldg(p.rope_cos + (size_t)pos * p.hd + j + half), s1 = __ldg(p.rope_sin + (size_t)pos * p.hd + j + half);
+        o0 = __fadd_rn(__fmul_rn(v0, c0), __fmul_rn(-v1, s0));
+        o1 = __fadd_rn(__fmul_rn(v1, c1), __fmul_rn(v0, s1));
+      }
+      if (which == 0) {
+        p.out[(size_t)b * p.Hq * p.hd + h * p.hd + j] = o0;
+        p.out[(size_t)b * p.Hq * p.hd + h * p.hd + j + half] = o1;
+      } else {
+        const int page = __ldg(p.block_table + b * p.pages_per_row + pos / kPageTokens);
+        float* dst = p.kv + kv_off(page, which - 1, h, pos % kPageTokens, p.Hkv, p.hd);
+        dst[j] = o0; dst[j + half] = o1;
+      }
+    } else if (EPI == EPI_OPROJ) {
+      const int d = p.nrows;
+      p.xres[(size_t)b * d + r0] = __fadd_rn(ldg_cg(&p.xres[(size_t)b * d + r0]), v0);
+      if (r1_valid) p.xres[(size_t)b * d + r1] = __fadd_rn(ldg_cg(&p.xres[(size_t)b * d + r1]), v1);
+    } else if (EPI == EPI_GATEUP) {
+      // LlamaMLP: silu(gate) * up ; silu(x) = x / (1 + exp(-x))
+      const float sg = __fdiv_rn(v0, __fadd_rn(1.0f, expf(-v0)));
+      p.out[(size_t)b * p.I + task] = __fmul_rn(sg, v1);
+    } else {  // EPI_HEADS: logits rows ordered (b, q) like gpt.py:459-464
+      const int q0 = r0 / p.V, c0 = r0 % p.V;
+      p.out[((size_t)b * p.rows_per_item + q0) * p.V + c0] = v0;
+      if (r1_valid) {
+        const int q1 = (2 * task + 1) / p.V, c1 = (2 * task + 1) % p.V;
+        p.out[((size_t)b * p.rows_per_item + q1) * p.V + c1] = v1;
+      }
     }
-  } else if (EPI == EPI_OPROJ || EPI == EPI_DOWN) {
-    const int d = p.nrows;
-    p.xres[(size_t)b * d + r0] = __fadd_rn(ldg_cg(&p.xres[(size_t)b * d + r0]), v0);
-    if (r1_valid) p.xres[(size_t)b * d + r1] = __fadd_rn(ldg_cg(&p.xres[(size_t)b * d + r1]), v1);
-  } else if (EPI == EPI_GATEUP) {
-    // LlamaMLP: silu(gate) * up ; silu(x) = x / (1 + exp(-x))
-    const float sg = __fdiv_rn(v0, __fadd_rn(1.0f, expf(-v0)));
-    p.out[(size_t)b * p.I + task] = __fmul_rn(sg, v1);
-  } else {  // EPI_HEADS: logits rows ordered (b, q) like gpt.py:459-464
-    const int q0 = r0 / p.V, c0 = r0 % p.V;
-    p.out[((size_t)b * p.rows_per_item + q0) * p.V + c0] = v0;
-    if (r1_valid) {
-      const int q1 = r1 / p.V, c1 = r1 % p.V;
-      p.out[((size_t)b * p.rows_per_item + q1) * p.V + c1] = v1;
+  }
+
+  if (EPI == EPI_DOWN) {
+    cluster_sync_all();  // every rank's partials are in its shared memory
+    if (kc == 0) {
+      const int d = p.nrows;
+      int j = 0;
+      for (int task = task0; task < p.ntasks && j < DOWN_MAX_TASKS; task += tstride, ++j) {
+        if ((lane % LPB) != 0 || (lane / LPB) >= nb) continue;
+        const int b = bbase + lane / LPB;
+        const float* r = red + ((warp * DOWN_MAX_TASKS + j) * 2) * BT + lane / LPB;
+        float v0 = r[0], v1 = r[BT];
+#pragma unroll
+        for (uint32_t rk = 1; rk < DOWN_SPLIT; ++rk) {  // fixed order: chunk 0 + 1 + 2 + 3
+          v0 = __fadd_rn(v0, ld_dsmem(r, rk));
+          v1 = __fadd_rn(v1, ld_dsmem(r + BT, rk));
+        }
+        const int r0 = 2 * task, r1 = 2 * task + 1;
+        p.xres[(size_t)b * d + r0] = __fadd_rn(ldg_cg(&p.xres[(size_t)b * d + r0]), v0);
+        if (r1 < d) p.xres[(size_t)b * d + r1] = __fadd_rn(ldg_cg(&p.xres[(size_t)b * d + r1]), v1);
+      }
     }
+    cluster_sync_all();  // keep the other ranks' shared memory alive until rank 0 has read it
   }
 }
 

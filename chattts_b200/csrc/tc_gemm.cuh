@@ -1,0 +1,250 @@
+// tcgen05 / TMEM / TMA GEMM with fp32-equivalent accuracy (3xTF32) for the dense contractions of
+// hot path 2 (and prefill):   C[m, n] = epi( sum_kk A[m, kk] * W[n, kk] )
+//
+//   * A: time-major activations [B][F][lda] fp32, read by a 3-D TMA tensor map (c, f, b).  A Conv1d tap
+//     is a shift of the f coordinate; frames outside [0, F) are zero-filled by TMA = the conv's zero
+//     padding, per utterance - no im2col, no boundary code.
+//   * W: [N][K] fp32, pre-split on the host into tf32-rounded `hi` and `lo = tf32(w - hi)` copies (weights
+//     are constants), two 2-D TMA maps.
+//   * 3xTF32:  A*W ~= A_hi*W_hi + A_hi*W_lo + A_lo*W_hi, accumulated in fp32 in TMEM.  A is split in
+//     shared memory by the 4 worker warps (cvt.rna.tf32), which later run the epilogue.
+//   * warp roles: 0-3 workers (split A, epilogue: tcgen05.ld -> bias/GELU/... -> global), 4 = TMA producer,
+//     5 = MMA issuer (one elected lane issues tcgen05.mma.cta_group::1.kind::tf32, M=128, N=128, K=8).
+//   * tile 128 (frames of one utterance) x 128 (channels) x 32 (k) per stage, 3 stages of 64 KiB:
+//     [A | A_lo | W_hi | W_lo], 128-byte swizzle (TMA and UMMA descriptors agree).
+#pragma once
+#include <cuda.h>
+
+#include "decoder_kernels.cuh"
+
+namespace ctb {
+
+constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32, TC_STAGES = 3;
+constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;          // 16 KiB
+constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;         // A, A_lo, W_hi, W_lo
+constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int TC_THREADS = 192;
+
+struct TcGemmP {
+  int N, K;                   // K = taps * Cin, multiple of 32
+  int taps, Cin, dil, pad, F, B;
+  const float* bias; const float* gamma;
+  const float* res; int ldres;
+  float* C; int ldc;
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {}
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// K-major, 128-byte swizzle shared-memory operand descriptor (cute::UMMA::SmemDescriptor layout):
+// start>>4 [0,14) | LBO>>4 [16,30) (=1, unused for swizzled K-major) | SBO>>4 [32,46) (= 1024 B between
+// 8-row groups) | version=1 [46,48) | layout SWIZZLE_128B = 2 [61,64)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 (1<<4), A=B=tf32 (2<<7, 2<<10), K-major both,
+// N>>3 at [17,23), M>>4 at [24,29)
+__device__ __forceinline__ uint32_t umma_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc),
+      "r"(accum) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_tc_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_whi,
+          const __grid_constant__ CUtensorMap map_wlo, const TcGemmP p) {
+  extern __shared__ uint8_t tc_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_STAGES * TC_STAGE_BYTES);
+  uint64_t* full = bars;                  // [stages]  TMA bytes landed
+  uint64_t* split = bars + TC_STAGES;     // [stages]  A split into hi / lo by the workers
+  uint64_t* empty = bars + 2 * TC_STAGES; // [stages]  MMAs of the stage retired
+  uint64_t* accum_full = bars + 3 * TC_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * TC_STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_per_utt = (p.F + TC_BM - 1) / TC_BM;
+  const int b = blockIdx.y / tiles_per_utt, f0 = (blockIdx.y % tiles_per_utt) * TC_BM;
+  const int n0 = blockIdx.x * TC_BN;
+  const int nk = p.K / TC_BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&split[s], 128); mbar_init(&empty[s], 1); }
+    mbar_init(accum_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 5) {  // TMEM: 128 fp32 accumulator columns
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TC_BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    // ===================== TMA producer
+    if (lane == 0) {
+      for (int t = 0; t < nk; ++t) {
+        const int s = t % TC_STAGES, it = t / TC_STAGES;
+        if (it > 0) mbar_wait(&empty[s], (it - 1) & 1);
+        uint8_t* st = smem + s * TC_STAGE_BYTES;
+        const int k0 = t * TC_BK;
+        const int tap = k0 / p.Cin, c0 = k0 - tap * p.Cin;
+        mbar_expect_tx(&full[s], 3 * TC_TILE_BYTES);
+        tma_load_3d(st, &map_a, &full[s], c0, f0 + (tap - p.pad) * p.dil, b);
+        tma_load_2d(st + 2 * TC_TILE_BYTES, &map_whi, &full[s], k0, n0);
+        tma_load_2d(st + 3 * TC_TILE_BYTES, &map_wlo, &full[s], k0, n0);
+      }
+    }
+  } else if (warp == 5) {
+    // ===================== MMA issuer
+    const uint32_t idesc = umma_idesc_tf32(TC_BM, TC_BN);
+    for (int t = 0; t < nk; ++t) {
+      const int s = t % TC_STAGES, it = t / TC_STAGES;
+      mbar_wait(&split[s], it & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t st = smem_u32(smem + s * TC_STAGE_BYTES);
+        const uint32_t a_hi = st, a_lo = st + TC_TILE_BYTES, w_hi = st + 2 * TC_TILE_BYTES, w_lo = st + 3 * TC_TILE_BYTES;
+#pragma unroll
+        for (int k = 0; k < TC_BK / 8; ++k) {
+          const uint32_t ko = k * 32;  // 8 tf32 = 32 bytes inside the 128-byte swizzle row
+          umma_tf32(tmem_base, umma_desc_sw128(a_hi + ko), umma_desc_sw128(w_hi + ko), idesc, (t | k) ? 1u : 0u);
+          umma_tf32(tmem_base, umma_desc_sw128(a_hi + ko), umma_desc_sw128(w_lo + ko), idesc, 1u);
+          umma_tf32(tmem_base, umma_desc_sw128(a_lo + ko), umma_desc_sw128(w_hi + ko), idesc, 1u);
+        }
+        umma_commit(&empty[s]);
+        if (t == nk - 1) umma_commit(accum_full);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===================== workers: split A, then epilogue
+    for (int t = 0; t < nk; ++t) {
+      const int s = t % TC_STAGES, it = t / TC_STAGES;
+      mbar_wait(&full[s], it & 1);
+      float4* a = reinterpret_cast<float4*>(smem + s * TC_STAGE_BYTES);
+      float4* lo = reinterpret_cast<float4*>(smem + s * TC_STAGE_BYTES + TC_TILE_BYTES);
+#pragma unroll
+      for (int j = 0; j < TC_TILE_BYTES / 16 / 128; ++j) {
+        const int i = threadIdx.x + 128 * j;  // elementwise: the swizzle pattern is the same in both tiles
+        const float4 v = a[i];
+        float4 h, l;
+        h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
+        l.x = to_tf32(v.x - h.x); l.y = to_tf32(v.y - h.y); l.z = to_tf32(v.z - h.z); l.w = to_tf32(v.w - h.w);
+        a[i] = h; lo[i] = l;
+      }
+      fence_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
+      mbar_arrive(&split[s]);
+    }
+    mbar_wait(accum_full, 0);
+    tc_fence_after();
+    const int row = warp * 32 + lane;  // TMEM lane == tile row; warp w may touch lanes [32w, 32w+32)
+    const int f = f0 + row;
+    const size_t m = (size_t)b * p.F + f;
+#pragma unroll 1
+    for (int cb = 0; cb < TC_BN / 32; ++cb) {
+      uint32_t r[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + cb * 32;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,"
+          "%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+            "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+            "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+            "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (f < p.F) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int n = n0 + cb * 32 + q * 4;
+          if (n >= p.N) continue;
+          float v[4] = {__uint_as_float(r[q * 4]), __uint_as_float(r[q * 4 + 1]), __uint_as_float(r[q * 4 + 2]),
+                        __uint_as_float(r[q * 4 + 3])};
+          if (EPI == GE_BIAS || EPI == GE_GELU || EPI == GE_SCALE_RES || EPI == GE_SPEC) {
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+            v[0] += bb.x; v[1] += bb.y; v[2] += bb.z; v[3] += bb.w;
+          }
+          if (EPI == GE_GELU) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = gelu_erf(v[j]);
+          } else if (EPI == GE_SCALE_RES) {
+            const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma + n));
+            const float4 rr = *reinterpret_cast<const float4*>(p.res + m * p.ldres + n);
+            v[0] = __fadd_rn(__fmul_rn(v[0], g.x), rr.x); v[1] = __fadd_rn(__fmul_rn(v[1], g.y), rr.y);
+            v[2] = __fadd_rn(__fmul_rn(v[2], g.z), rr.z); v[3] = __fadd_rn(__fmul_rn(v[3], g.w), rr.w);
+          } else if (EPI == GE_COEF) {
+            const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma + n));
+            v[0] *= g.x; v[1] *= g.y; v[2] *= g.z; v[3] *= g.w;
+          } else if (EPI == GE_SPEC) {
+#pragma unroll
+            for (int j = 0; j < 4; j += 2) {
+              const float mag = fminf(expf(v[j]), 100.0f);
+              float sn, cs;
+              sincosf(v[j + 1], &sn, &cs);
+              v[j] = mag * cs; v[j + 1] = mag * sn;
+            }
+          }
+          *reinterpret_cast<float4*>(p.C + m * p.ldc + n) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TC_BN));
+  }
+}
+
+}  // namespace ctb

@@ -100,7 +100,7 @@ def idft_basis(n_fft: int, window: torch.Tensor, spec_k: int) -> torch.Tensor:
 def pack_vocos(s: State, cfg: VocosConfig) -> torch.Tensor:
     pk = _Packer()
     nbin = cfg.n_fft // 2 + 1
-    spec_k = (cfg.n_fft + 2 + 15) // 16 * 16
+    spec_k = (cfg.n_fft + 2 + 31) // 32 * 32
     pk.add(_tap_major(s["backbone.embed.weight"], MEL_PAD))
     pk.add(s["backbone.embed.bias"])
     pk.add(s["backbone.norm.weight"])

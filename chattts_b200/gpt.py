@@ -303,6 +303,8 @@ class GPT:
                 _lib.check(lib.ctb_gpt_decode(self._handle, n, stream_ptr))
                 query()
                 done = st.steps_done
+                if done <= steps and not st.all_finished:
+                    raise _lib.CtbError(f"decode made no progress (steps_done={done}); device loop state is corrupt")
                 if pbar is not None:
                     pbar.update(done - steps)
                 steps = done

@@ -118,3 +118,26 @@ def test_full_size_properties_10s_batch():
     assert torch.equal(solo[0], wav[2])  # rows never interact
     ref = O.vocos_decode(O.dvae_decode(x[:1].permute(0, 2, 1).contiguous(), m["ds"]), m["vs"])
     assert rms(wav[:1].cpu(), ref) < 1e-4
+
+
+def test_tensor_core_path_matches_fma_path():
+    """The tcgen05 3xTF32 GEMMs (default) against the plain fp32 FMA GEMMs (CTB_DECODER_FMA=1) on the same
+    handle configuration: fp32-equivalent accuracy is the contract of the hi/lo split."""
+    import os
+
+    from chattts_b200.decoder import DVAE, Vocos
+
+    m = models()
+    x = torch.randn(2, 300, 768, generator=torch.Generator().manual_seed(3))
+    wav_tc = m["dec"].engine.tokens_to_wav(x, 1)
+    os.environ["CTB_DECODER_FMA"] = "1"
+    try:
+        voc = Vocos(CFG.vocos, "cuda", max_batch=2, max_tokens=300).load_state_dict(m["vs"])
+        dec = DVAE(CFG.decoder, dim=384, device="cuda", vocos=voc, max_batch=2, max_tokens=300).load_state_dict(m["ds"])
+        wav_fma = dec.engine.tokens_to_wav(x, 1)
+        mel_fma = dec.engine.dvae_decode(x, 1)
+    finally:
+        del os.environ["CTB_DECODER_FMA"]
+    mel_tc = m["dec"].engine.dvae_decode(x, 1)
+    assert (mel_tc - mel_fma).abs().max() < 2e-5 * max(1.0, float(mel_fma.abs().max()))
+    assert rms(wav_tc, wav_fma) < 1e-5 * max(1e-3, float(wav_fma.pow(2).mean().sqrt())) + 1e-7

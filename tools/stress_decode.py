@@ -1,0 +1,30 @@
+"""Stress / timing helper: repeated device-resident generate() passes at a given batch (no oracle)."""
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from bench import build_inputs
+from chattts_b200.config import Config
+from chattts_b200.embed import Embed
+from chattts_b200.gpt import GPT
+from chattts_b200.synth import synth_embed_state, synth_gpt_state
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 1
+tokens = int(sys.argv[2]) if len(sys.argv) > 2 else 512
+reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+dev = torch.device("cuda")
+embed = Embed(768, 626, 21178, 4).load_state_dict(synth_embed_state(1)).to(dev)
+gpt = GPT(Config().gpt, embed, device=dev, device_gpt=dev, max_batch=max(B, 1), max_context=16 + tokens + 16)
+gpt.load_state(synth_gpt_state(0))
+ids, mask, tmask, procs, scfg, q = build_inputs(B, tokens, seed=1)
+emb_d, mask_d, q_d = embed(ids, tmask).to(dev), mask.to(dev).to(torch.uint8), q.to(dev)
+ids_out = torch.zeros(B, tokens, 4, dtype=torch.int32, device=dev)
+for r in range(reps):
+    t = time.time()
+    gpt.enqueue_generate(emb_d, mask_d, scfg, q_d, tokens, False, ids_out, None)
+    torch.cuda.synchronize()
+    dt = time.time() - t
+    print(f"B={B} rep {r}: {dt*1e3:.1f} ms  {dt*1e6/(tokens+15):.1f} us/step  ids[0,-1]={ids_out[0,-1].tolist()}", flush=True)
