@@ -3,8 +3,11 @@
 
 #include <vector>
 
+#include <cudaTypedefs.h>
+
 #define CTB_GPT_KERNELS_IMPL
 #include "gpt_kernels.cuh"
+#include "tc_decode.cuh"
 
 namespace ctb {
 
@@ -54,6 +57,14 @@ struct ctb_gpt {
   float* hiddens_out;
   cudaGraphExec_t graph_exec;
   cudaStream_t cap_stream;
+  // ---- tensor-core decode path (tc_decode.cuh)
+  bool use_tc, tc_ready;
+  int tc_min_batch;
+  float *tc_wqkv, *tc_wgu, *tc_heads_code, *tc_heads_text;  // permuted / norm-folded weight copies
+  float *x_hi, *x_lo, *attn_hi, *attn_lo, *h_hi, *h_lo;      // [32][K] tf32-split activations
+  CUtensorMap *m_wqkv, *m_wo, *m_wgu, *m_wd;                 // [layers] host arrays
+  CUtensorMap m_hcode, m_htext;
+  CUtensorMap m_x[2][2], m_attn[2][2], m_h[2][2];            // [npad16|32][hi|lo]
   bool use_graph;
 };
 
@@ -90,6 +101,106 @@ template <typename T>
 static int dalloc(T** p, size_t n) {
   CTB_CUDA(cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T)));
   CTB_CUDA(cudaMemset(*p, 0, n * sizeof(T)));
+  return CTB_OK;
+}
+
+namespace ctb {
+__global__ void k_build_tc_weight(const float* __restrict__ W, const float* __restrict__ scale, float* __restrict__ out,
+                                  int rows, int K, int mode, int qk_rows, int hd, int I) {
+  const int r = blockIdx.x;
+  if (r >= rows) return;
+  int pr = r;
+  if (mode == 1 && r < qk_rows) {
+    const int h = r / hd, j = r % hd, half = hd / 2;
+    pr = h * hd + (j < half ? 2 * j : 2 * (j - half) + 1);
+  } else if (mode == 2) {
+    pr = (r < I) ? 2 * r : 2 * (r - I) + 1;
+  }
+  for (int k = threadIdx.x; k < K; k += blockDim.x)
+    out[(size_t)pr * K + k] = scale ? __fmul_rn(W[(size_t)r * K + k], scale[k]) : W[(size_t)r * K + k];
+}
+}  // namespace ctb
+
+static int encode_map_2d(CUtensorMap* m, const float* base, uint64_t rows, uint64_t K, uint32_t box_rows) {
+  static PFN_cuTensorMapEncodeTiled_v12000 enc = nullptr;
+  if (!enc) {
+    void* fp = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return set_err(CTB_ERR_CUDA, "cuTensorMapEncodeTiled unavailable");
+    enc = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fp);
+  }
+  const cuuint64_t dims[2] = {K, rows};
+  const cuuint64_t strides[1] = {K * 4};
+  const cuuint32_t box[2] = {32, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_err(CTB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return CTB_OK;
+}
+
+template <int EPI, int NPAD, int CS>
+static int set_tc_attr() {
+  CTB_CUDA(cudaFuncSetAttribute(k_tc_dec<EPI, NPAD, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                TdCfg<NPAD>::SMEM_BYTES));
+  return CTB_OK;
+}
+
+// cluster sizes of the split-K (K slices per 128-row tile)
+constexpr int CS_QKV = 4, CS_O = 8, CS_GU = 2, CS_DOWN = 8, CS_HEADS = 4;
+
+static int tc_setup(ctb_gpt* h) {
+  const ctb_gpt_config& c = h->cfg;
+  const ctb_gpt_layout& L = h->lay;
+  const size_t d = c.hidden_size, I = c.intermediate_size;
+  const size_t nqkv = (size_t)(c.num_heads + 2 * c.num_kv_heads) * c.head_dim;
+  int rc;
+  if ((rc = dalloc(&h->tc_wqkv, (size_t)c.num_layers * nqkv * d))) return rc;
+  if ((rc = dalloc(&h->tc_wgu, (size_t)c.num_layers * 2 * I * d))) return rc;
+  if ((rc = dalloc(&h->tc_heads_code, (size_t)c.num_vq * c.num_audio_tokens * d))) return rc;
+  if ((rc = dalloc(&h->tc_heads_text, (size_t)c.num_text_tokens * d))) return rc;
+  if ((rc = dalloc(&h->x_hi, 32 * d))) return rc;
+  if ((rc = dalloc(&h->x_lo, 32 * d))) return rc;
+  if ((rc = dalloc(&h->attn_hi, 32 * d))) return rc;
+  if ((rc = dalloc(&h->attn_lo, 32 * d))) return rc;
+  if ((rc = dalloc(&h->h_hi, 32 * I))) return rc;
+  if ((rc = dalloc(&h->h_lo, 32 * I))) return rc;
+  h->m_wqkv = new CUtensorMap[c.num_layers]; h->m_wo = new CUtensorMap[c.num_layers];
+  h->m_wgu = new CUtensorMap[c.num_layers]; h->m_wd = new CUtensorMap[c.num_layers];
+  const int qk_rows = (c.num_heads + c.num_kv_heads) * c.head_dim;
+  for (int l = 0; l < c.num_layers; ++l) {
+    const float* Wl = h->W + L.layer0 + (int64_t)l * L.layer_stride;
+    float* wq = h->tc_wqkv + (size_t)l * nqkv * d;
+    float* wg = h->tc_wgu + (size_t)l * 2 * I * d;
+    k_build_tc_weight<<<(unsigned)nqkv, 256>>>(Wl + L.wqkv, Wl + L.ln1, wq, (int)nqkv, (int)d, 1, qk_rows, c.head_dim, 0);
+    k_build_tc_weight<<<(unsigned)(2 * I), 256>>>(Wl + L.wgate_up, Wl + L.ln2, wg, (int)(2 * I), (int)d, 2, 0, 0, (int)I);
+    if ((rc = encode_map_2d(&h->m_wqkv[l], wq, nqkv, d, 128))) return rc;
+    if ((rc = encode_map_2d(&h->m_wo[l], Wl + L.wo, d, (size_t)c.num_heads * c.head_dim, 128))) return rc;
+    if ((rc = encode_map_2d(&h->m_wgu[l], wg, 2 * I, d, 128))) return rc;
+    if ((rc = encode_map_2d(&h->m_wd[l], Wl + L.wdown, d, I, 128))) return rc;
+  }
+  const int nhc = c.num_vq * c.num_audio_tokens;
+  k_build_tc_weight<<<nhc, 256>>>(h->W + L.head_code, h->W + L.final_norm, h->tc_heads_code, nhc, (int)d, 0, 0, 0, 0);
+  k_build_tc_weight<<<c.num_text_tokens, 256>>>(h->W + L.head_text, h->W + L.final_norm, h->tc_heads_text,
+                                                c.num_text_tokens, (int)d, 0, 0, 0, 0);
+  CTB_CUDA(cudaDeviceSynchronize());
+  if ((rc = encode_map_2d(&h->m_hcode, h->tc_heads_code, nhc, d, 128))) return rc;
+  if ((rc = encode_map_2d(&h->m_htext, h->tc_heads_text, c.num_text_tokens, d, 128))) return rc;
+  for (int n = 0; n < 2; ++n) {
+    const uint32_t npad = n ? 32 : 16;
+    if ((rc = encode_map_2d(&h->m_x[n][0], h->x_hi, 32, d, npad))) return rc;
+    if ((rc = encode_map_2d(&h->m_x[n][1], h->x_lo, 32, d, npad))) return rc;
+    if ((rc = encode_map_2d(&h->m_attn[n][0], h->attn_hi, 32, d, npad))) return rc;
+    if ((rc = encode_map_2d(&h->m_attn[n][1], h->attn_lo, 32, d, npad))) return rc;
+    if ((rc = encode_map_2d(&h->m_h[n][0], h->h_hi, 32, I, npad))) return rc;
+    if ((rc = encode_map_2d(&h->m_h[n][1], h->h_lo, 32, I, npad))) return rc;
+  }
+#define TCATTR(E, C) if ((rc = set_tc_attr<E, 16, C>())) return rc; if ((rc = set_tc_attr<E, 32, C>())) return rc;
+  TCATTR(DE_QKV, CS_QKV) TCATTR(DE_OPROJ, CS_O) TCATTR(DE_GATEUP, CS_GU) TCATTR(DE_DOWN, CS_DOWN) TCATTR(DE_HEADS, CS_HEADS)
+#undef TCATTR
   return CTB_OK;
 }
 
@@ -148,6 +259,12 @@ extern "C" int ctb_gpt_create(const ctb_gpt_config* c, const float* weights_dev,
   for (size_t i = 0; i < bt_host.size(); ++i) bt_host[i] = (int)i;
   cudaMemcpy(h->block_table, bt_host.data(), bt_host.size() * sizeof(int), cudaMemcpyHostToDevice);
   h->use_graph = getenv("CTB_NO_GRAPH") == nullptr;
+  // tensor-core decode GEMMs (tc_decode.cuh): CTB_GPT_TC=1 forces them for every batch, CTB_GPT_FMA=1 disables
+  // them; by default they serve batches > 16 rows, where the fp32 FMA path turns compute-bound.
+  h->tc_ready = getenv("CTB_GPT_FMA") == nullptr && c->max_batch <= 32 &&
+                (getenv("CTB_GPT_TC") != nullptr || c->max_batch > 16);
+  h->tc_min_batch = getenv("CTB_GPT_TC") != nullptr ? 1 : 17;
+  if (h->tc_ready && (rc = tc_setup(h)) != CTB_OK) { ctb_gpt_destroy(h); return rc; }
   *out = h;
   return CTB_OK;
 }
@@ -157,7 +274,9 @@ extern "C" int ctb_gpt_destroy(ctb_gpt* h) {
   if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   void* ptrs[] = {h->x, h->qbuf, h->attn, h->mlp, h->logits, h->kv, h->part, h->block_table, h->seq_len,
-                  h->pos, h->counter, h->end_idx, h->idx, h->active, h->finish, h->st};
+                  h->pos, h->counter, h->end_idx, h->idx, h->active, h->finish, h->st, h->tc_wqkv, h->tc_wgu,
+                  h->tc_heads_code, h->tc_heads_text, h->x_hi, h->x_lo, h->attn_hi, h->attn_lo, h->h_hi, h->h_lo};
+  delete[] h->m_wqkv; delete[] h->m_wo; delete[] h->m_wgu; delete[] h->m_wd;
   for (void* p : ptrs) if (p) cudaFree(p);
   delete h;
   return CTB_OK;
@@ -233,6 +352,7 @@ static StepCtx make_ctx(ctb_gpt* h, int decode) {
   AttnP& a = x.a;
   a.st = h->st; a.check_finished = decode; a.q = h->qbuf; a.block_table = h->block_table;
   a.pages_per_row = h->pages_per_row; a.pos = h->pos; a.active = h->active; a.out = h->attn; a.part = h->part;
+  a.out_hi = h->use_tc ? h->attn_hi : nullptr; a.out_lo = h->use_tc ? h->attn_lo : nullptr;
   a.counter = h->counter; a.Hq = c.num_heads; a.Hkv = c.num_kv_heads; a.hd = c.head_dim;
   a.nsplit_max = h->nsplit_max; a.scaling = 1.0f / sqrtf((float)c.head_dim);
   return x;
@@ -256,7 +376,10 @@ static int launch_layer_kernel(ctb_gpt* h, const StepCtx& x, int l, int kind, cu
       a.kv = kvl;
       // context after this call <= T0 + max_new: only launch splits that can be populated
       const int max_ctx = std::min(c.max_context, h->T0 + h->max_new);
-      dim3 agrid((max_ctx + ATT_CHUNK - 1) / ATT_CHUNK, c.num_heads, h->B);
+      // enough CTAs to fill the chip twice; a CTA walks chunks c, c + grid.x, ... with a running softmax,
+      // so large batches need no cross-CTA merge at all
+      const int want = (2 * g_num_sms + c.num_heads * h->B - 1) / (c.num_heads * h->B);
+      dim3 agrid(std::max(1, std::min(want, (max_ctx + ATT_CHUNK - 1) / ATT_CHUNK)), c.num_heads, h->B);
       CTB_CUDA(launch_pdl(k_attn, agrid, dim3(ATT_THREADS), 0, s, a));
       CTB_LAUNCH_CHECK();
       return CTB_OK;
@@ -298,6 +421,65 @@ static int launch_sampler(ctb_gpt* h, const StepCtx& x, cudaStream_t s) {
   return launch_sample(sp, s);
 }
 
+template <int EPI, int CS>
+static int launch_tc(int npad, const CUtensorMap& mw, const CUtensorMap& mxh, const CUtensorMap& mxl, const TcDecP& p,
+                     cudaStream_t s) {
+  const int tiles = (p.nrows + 127) / 128;
+  dim3 grid(tiles * CS);
+  if (npad == 16)
+    CTB_CUDA(launch_pdl_cluster(k_tc_dec<EPI, 16, CS>, grid, dim3(TD_THREADS), (size_t)TdCfg<16>::SMEM_BYTES, s, (unsigned)CS, mw, mxh, mxl, p));
+  else
+    CTB_CUDA(launch_pdl_cluster(k_tc_dec<EPI, 32, CS>, grid, dim3(TD_THREADS), (size_t)TdCfg<32>::SMEM_BYTES, s, (unsigned)CS, mw, mxh, mxl, p));
+  CTB_LAUNCH_CHECK();
+  return CTB_OK;
+}
+
+static TcDecP make_tc(ctb_gpt* h) {
+  const ctb_gpt_config& c = h->cfg;
+  TcDecP p{};
+  p.B = h->B; p.eps = c.rms_eps; p.d = c.hidden_size; p.xres = h->x; p.x_hi = h->x_hi; p.x_lo = h->x_lo;
+  p.qbuf = h->qbuf; p.block_table = h->block_table; p.pages_per_row = h->pages_per_row; p.pos = h->pos;
+  p.active = h->active; p.rope_cos = h->W + h->lay.rope_cos; p.rope_sin = h->W + h->lay.rope_sin;
+  p.Hq = c.num_heads; p.Hkv = c.num_kv_heads; p.hd = c.head_dim; p.h_hi = h->h_hi; p.h_lo = h->h_lo;
+  p.I = c.intermediate_size; p.st = h->st;
+  return p;
+}
+
+static int launch_layer_kernel_tc(ctb_gpt* h, int l, int kind, cudaStream_t s) {
+  const ctb_gpt_config& c = h->cfg;
+  const int n = h->B > 16 ? 1 : 0, npad = n ? 32 : 16;
+  const int d = c.hidden_size, I = c.intermediate_size;
+  TcDecP p = make_tc(h);
+  switch (kind) {
+    case 0:
+      p.K = d; p.kslice = d / CS_QKV; p.nrows = (c.num_heads + 2 * c.num_kv_heads) * c.head_dim; p.xraw = h->x;
+      p.kv = h->kv + (size_t)l * h->kv_layer_floats;
+      return launch_tc<DE_QKV, CS_QKV>(npad, h->m_wqkv[l], h->m_x[n][0], h->m_x[n][1], p, s);
+    case 2:
+      p.K = c.num_heads * c.head_dim; p.kslice = p.K / CS_O; p.nrows = d; p.xraw = nullptr;
+      return launch_tc<DE_OPROJ, CS_O>(npad, h->m_wo[l], h->m_attn[n][0], h->m_attn[n][1], p, s);
+    case 3:
+      p.K = d; p.kslice = d / CS_GU; p.nrows = 2 * I; p.xraw = h->x;
+      return launch_tc<DE_GATEUP, CS_GU>(npad, h->m_wgu[l], h->m_x[n][0], h->m_x[n][1], p, s);
+    case 4:
+      p.K = I; p.kslice = I / CS_DOWN; p.nrows = d; p.xraw = nullptr;
+      return launch_tc<DE_DOWN, CS_DOWN>(npad, h->m_wd[l], h->m_h[n][0], h->m_h[n][1], p, s);
+  }
+  return set_err(CTB_ERR_ARG, "bad tc kernel kind %d", kind);
+}
+
+static int launch_heads_tc(ctb_gpt* h, cudaStream_t s) {
+  const ctb_gpt_config& c = h->cfg;
+  const int n = h->B > 16 ? 1 : 0, npad = n ? 32 : 16;
+  TcDecP p = make_tc(h);
+  const int rpi = h->infer_text ? 1 : c.num_vq;
+  const int V = h->infer_text ? c.num_text_tokens : c.num_audio_tokens;
+  p.K = c.hidden_size; p.kslice = p.K / CS_HEADS; p.nrows = rpi * V; p.xraw = h->x;
+  p.logits = h->logits; p.rows_per_item = rpi; p.V = V; p.hidden_out = h->hiddens_out;
+  p.hidden_stride = h->max_new * c.hidden_size; p.final_norm_w = h->W + h->lay.final_norm;
+  return launch_tc<DE_HEADS, CS_HEADS>(npad, h->infer_text ? h->m_htext : h->m_hcode, h->m_x[n][0], h->m_x[n][1], p, s);
+}
+
 // One loop iteration.  col >= 0: prefill column `col` of the prompt; col < 0: decode step.
 // sample: run heads + sampler + finalize (last prompt column and every decode step).
 static int enqueue_step(ctb_gpt* h, int col, bool sample, cudaStream_t s) {
@@ -313,15 +495,17 @@ static int enqueue_step(ctb_gpt* h, int col, bool sample, cudaStream_t s) {
   ip.ids_out = h->ids_out; ip.max_new = h->max_new; ip.num_vq = c.num_vq; ip.num_audio = c.num_audio_tokens;
   ip.infer_text = h->infer_text;
   ip.x = h->x; ip.seq_len = h->seq_len; ip.pos = h->pos; ip.active = h->active;
+  ip.x_hi = h->use_tc ? h->x_hi : nullptr; ip.x_lo = h->use_tc ? h->x_lo : nullptr;
   CTB_CUDA(launch_pdl(k_input, dim3(h->B), dim3(256), 0, s, ip));
   CTB_LAUNCH_CHECK();
 
   const StepCtx x = make_ctx(h, decode);
   for (int l = 0; l < c.num_layers; ++l)
     for (int kind = 0; kind < 5; ++kind)
-      if ((rc = launch_layer_kernel(h, x, l, kind, s))) return rc;
+      if ((rc = (h->use_tc && kind != 1) ? launch_layer_kernel_tc(h, l, kind, s) : launch_layer_kernel(h, x, l, kind, s)))
+        return rc;
   if (!sample) return CTB_OK;
-  if ((rc = launch_heads(h, x, s))) return rc;
+  if ((rc = h->use_tc ? launch_heads_tc(h, s) : launch_heads(h, x, s))) return rc;
   if ((rc = launch_sampler(h, x, s))) return rc;
 
   FinalP fp{};
@@ -343,10 +527,11 @@ extern "C" int ctb_gpt_profile_kernel(ctb_gpt* h, int32_t kind, void* stream) {
   StepCtx x = make_ctx(h, 0);
   x.g.check_finished = 0; x.a.check_finished = 0;
   int rc;
-  if (kind == 5) return launch_heads(h, x, s);
+  if (kind == 5) return h->use_tc ? launch_heads_tc(h, s) : launch_heads(h, x, s);
   if (kind == 6) return launch_sampler(h, x, s);
   for (int l = 0; l < h->cfg.num_layers; ++l)
-    if ((rc = launch_layer_kernel(h, x, l, kind, s))) return rc;
+    if ((rc = (h->use_tc && kind != 1) ? launch_layer_kernel_tc(h, l, kind, s) : launch_layer_kernel(h, x, l, kind, s)))
+      return rc;
   return CTB_OK;
 }
 
@@ -360,6 +545,7 @@ extern "C" int ctb_gpt_begin(ctb_gpt* h, int32_t B, int32_t T0, const float* emb
   if (sampler->past_window > 31 || sampler->past_window < 0) return set_err(CTB_ERR_ARG, "past_window out of range");
   cudaStream_t s = (cudaStream_t)stream;
   h->B = B; h->T0 = T0; h->max_new = max_new_token; h->infer_text = infer_text ? 1 : 0;
+  h->use_tc = h->tc_ready && B >= h->tc_min_batch;
   h->sampler = *sampler; h->q_noise = q_noise_dev; h->emb = emb_dev; h->mask = mask_dev;
   h->ids_out = ids_out_dev; h->hiddens_out = hiddens_out_dev;
   if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
@@ -368,6 +554,13 @@ extern "C" int ctb_gpt_begin(ctb_gpt* h, int32_t B, int32_t T0, const float* emb
   CTB_CUDA(cudaMemsetAsync(h->finish, 0, h->bpad_max, s));
   CTB_CUDA(cudaMemsetAsync(h->end_idx, 0, sizeof(int) * h->bpad_max, s));
   CTB_CUDA(cudaMemsetAsync(h->counter, 0, sizeof(int) * h->cfg.max_batch * h->cfg.num_heads, s));
+  if (h->use_tc) {
+    const size_t d = h->cfg.hidden_size, I = h->cfg.intermediate_size;
+    float* z768[] = {h->x_hi, h->x_lo, h->attn_hi, h->attn_lo};
+    for (float* zp : z768) CTB_CUDA(cudaMemsetAsync(zp, 0, 32 * d * sizeof(float), s));
+    CTB_CUDA(cudaMemsetAsync(h->h_hi, 0, 32 * I * sizeof(float), s));
+    CTB_CUDA(cudaMemsetAsync(h->h_lo, 0, 32 * I * sizeof(float), s));
+  }
   int rc;
   // prefill: the prompt is walked column by column through the decode kernels (left padding
   // keeps every row's last prompt token in the last column, like the reference's batches)

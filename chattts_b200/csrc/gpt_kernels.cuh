@@ -292,6 +292,7 @@ struct InputP {
   const int32_t* ids_out; // [B, max_new, num_vq]
   int max_new, num_vq, num_audio, infer_text;
   float* x;               // [Bpad, d]
+  float* x_hi; float* x_lo; // tensor-core path: tf32 hi / lo split of x (nullptr on the FMA path)
   int* seq_len;           // [Bpad]
   int* pos;               // [Bpad]
   uint8_t* active;        // [Bpad]
@@ -326,6 +327,19 @@ __global__ void k_input(const InputP p) {
       }
     }
   }
+  if (p.x_hi != nullptr) {
+    __syncthreads();
+    for (int k = threadIdx.x; k < p.d; k += blockDim.x) {
+      const float v = x[k];
+      uint32_t hb;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
+      const float hi = __uint_as_float(hb);
+      uint32_t lb;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(v - hi));
+      p.x_hi[(size_t)b * p.d + k] = hi;
+      p.x_lo[(size_t)b * p.d + k] = __uint_as_float(lb);
+    }
+  }
   if (threadIdx.x == 0) {
     const int n = ldg_cg(&p.seq_len[b]);
     p.pos[b] = n;               // position id = #valid tokens before this one (gpt.py:234-241)
@@ -344,6 +358,7 @@ struct AttnP {
   const int* block_table; int pages_per_row;
   const int* pos; const uint8_t* active;
   float* out;            // [Bpad, Hq*hd]
+  float* out_hi; float* out_lo;  // tensor-core path copies (nullptr on the FMA path)
   float* part;           // [B, Hq, nsplit_max, hd + 2]
   int* counter;          // [B, Hq]
   int Hq, Hkv, hd, nsplit_max;
@@ -364,9 +379,20 @@ __global__ void __launch_bounds__(ATT_THREADS) k_attn(const AttnP p) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int HD = 64, NW = ATT_THREADS / 32, PER_WARP = ATT_CHUNK / NW, ITER = PER_WARP / 4;
   float* outp = p.out + (size_t)b * p.Hq * HD + h * HD;
-  if (!ldg_cg(&p.active[b])) { if (split == 0 && tid < HD) outp[tid] = 0.f; return; }
+  auto store_out = [&](float v) {
+    outp[tid] = v;
+    if (p.out_hi != nullptr) {
+      uint32_t hb, lb;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(v - __uint_as_float(hb)));
+      p.out_hi[(size_t)b * p.Hq * HD + h * HD + tid] = __uint_as_float(hb);
+      p.out_lo[(size_t)b * p.Hq * HD + h * HD + tid] = __uint_as_float(lb);
+    }
+  };
+  if (!ldg_cg(&p.active[b])) { if (split == 0 && tid < HD) store_out(0.f); return; }
   const int n = ldg_cg(&p.pos[b]) + 1;  // keys 0..pos
-  const int nsplit = (n + ATT_CHUNK - 1) / ATT_CHUNK;
+  const int nchunk = (n + ATT_CHUNK - 1) / ATT_CHUNK;
+  const int nsplit = min(nchunk, (int)gridDim.x);  // CTAs working on this (row, head): chunk c -> CTA c % gridDim.x
   if (split >= nsplit) return;
   const int hk = h / (p.Hq / p.Hkv);
   const int* bt = p.block_table + b * p.pages_per_row;
@@ -379,74 +405,81 @@ __global__ void __launch_bounds__(ATT_THREADS) k_attn(const AttnP p) {
   const float* qp = p.q + (size_t)b * p.Hq * HD + h * HD + sub * 8;
   const float4 q0 = ldg_cg(reinterpret_cast<const float4*>(qp));
   const float4 q1 = ldg_cg(reinterpret_cast<const float4*>(qp + 4));
-  const int tbase = split * ATT_CHUNK + warp * PER_WARP + grp;
-  float4 k0[ITER], k1[ITER], v0[ITER], v1[ITER];
-#pragma unroll
-  for (int i = 0; i < ITER; ++i) {
-    const int t = tbase + 4 * i;
-    k0[i] = k1[i] = v0[i] = v1[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (t < n) {
-      const int page = bt[t / kPageTokens];
-      const float* kr = p.kv + kv_off(page, 0, hk, t % kPageTokens, p.Hkv, HD) + sub * 8;
-      const float* vr = p.kv + kv_off(page, 1, hk, t % kPageTokens, p.Hkv, HD) + sub * 8;
-      k0[i] = ldg_cg(reinterpret_cast<const float4*>(kr));
-      k1[i] = ldg_cg(reinterpret_cast<const float4*>(kr + 4));
-      v0[i] = ldg_cg(reinterpret_cast<const float4*>(vr));
-      v1[i] = ldg_cg(reinterpret_cast<const float4*>(vr + 4));
-    }
-  }
-  float sc[ITER], m = -INFINITY;
-#pragma unroll
-  for (int i = 0; i < ITER; ++i) {
-    float s = q0.x * k0[i].x + q0.y * k0[i].y + q0.z * k0[i].z + q0.w * k0[i].w + q1.x * k1[i].x + q1.y * k1[i].y +
-              q1.z * k1[i].z + q1.w * k1[i].w;
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    s += __shfl_xor_sync(0xffffffffu, s, 2);
-    s += __shfl_xor_sync(0xffffffffu, s, 4);
-    sc[i] = (tbase + 4 * i < n) ? s * p.scaling : -INFINITY;
-    m = fmaxf(m, sc[i]);
-  }
-  m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
-  m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 16));
-  float l = 0.f, o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  if (m > -INFINITY) {
+  float M = -INFINITY, L = 0.f, O = 0.f;  // running softmax state of this CTA (thread d < 64 owns dim d)
+  for (int chunk = split; chunk < nchunk; chunk += gridDim.x) {
+    const int tbase = chunk * ATT_CHUNK + warp * PER_WARP + grp;
+    float4 k0[ITER], k1[ITER], v0[ITER], v1[ITER];
 #pragma unroll
     for (int i = 0; i < ITER; ++i) {
-      const float e = expf(sc[i] - m);  // exp(-inf) = 0 for masked keys
-      l += e;
-      o[0] = fmaf(e, v0[i].x, o[0]); o[1] = fmaf(e, v0[i].y, o[1]); o[2] = fmaf(e, v0[i].z, o[2]);
-      o[3] = fmaf(e, v0[i].w, o[3]); o[4] = fmaf(e, v1[i].x, o[4]); o[5] = fmaf(e, v1[i].y, o[5]);
-      o[6] = fmaf(e, v1[i].z, o[6]); o[7] = fmaf(e, v1[i].w, o[7]);
+      const int t = tbase + 4 * i;
+      k0[i] = k1[i] = v0[i] = v1[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (t < n) {
+        const int page = bt[t / kPageTokens];
+        const float* kr = p.kv + kv_off(page, 0, hk, t % kPageTokens, p.Hkv, HD) + sub * 8;
+        const float* vr = p.kv + kv_off(page, 1, hk, t % kPageTokens, p.Hkv, HD) + sub * 8;
+        k0[i] = ldg_cg(reinterpret_cast<const float4*>(kr));
+        k1[i] = ldg_cg(reinterpret_cast<const float4*>(kr + 4));
+        v0[i] = ldg_cg(reinterpret_cast<const float4*>(vr));
+        v1[i] = ldg_cg(reinterpret_cast<const float4*>(vr + 4));
+      }
     }
-  }
-  // merge the 4 key groups of the warp (same `sub`, different `grp`)
-  l += __shfl_xor_sync(0xffffffffu, l, 8);
-  l += __shfl_xor_sync(0xffffffffu, l, 16);
+    float sc[ITER], m = -INFINITY;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    o[j] += __shfl_xor_sync(0xffffffffu, o[j], 8);
-    o[j] += __shfl_xor_sync(0xffffffffu, o[j], 16);
-  }
-  if (lane < 8) {
-    *reinterpret_cast<float4*>(&s_o[warp][lane * 8]) = make_float4(o[0], o[1], o[2], o[3]);
-    *reinterpret_cast<float4*>(&s_o[warp][lane * 8 + 4]) = make_float4(o[4], o[5], o[6], o[7]);
-    if (lane == 0) { s_m[warp] = m; s_l[warp] = l; }
-  }
-  __syncthreads();
-  // ---- merge the warps: thread d < 64 owns output dim d
-  float M = -INFINITY, L = 0.f, O = 0.f;
-  if (tid < HD) {
+    for (int i = 0; i < ITER; ++i) {
+      float s = q0.x * k0[i].x + q0.y * k0[i].y + q0.z * k0[i].z + q0.w * k0[i].w + q1.x * k1[i].x + q1.y * k1[i].y +
+                q1.z * k1[i].z + q1.w * k1[i].w;
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      s += __shfl_xor_sync(0xffffffffu, s, 4);
+      sc[i] = (tbase + 4 * i < n) ? s * p.scaling : -INFINITY;
+      m = fmaxf(m, sc[i]);
+    }
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 16));
+    float l = 0.f, o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (m > -INFINITY) {
 #pragma unroll
-    for (int w = 0; w < NW; ++w) M = fmaxf(M, s_m[w]);
+      for (int i = 0; i < ITER; ++i) {
+        const float e = expf(sc[i] - m);  // exp(-inf) = 0 for masked keys
+        l += e;
+        o[0] = fmaf(e, v0[i].x, o[0]); o[1] = fmaf(e, v0[i].y, o[1]); o[2] = fmaf(e, v0[i].z, o[2]);
+        o[3] = fmaf(e, v0[i].w, o[3]); o[4] = fmaf(e, v1[i].x, o[4]); o[5] = fmaf(e, v1[i].y, o[5]);
+        o[6] = fmaf(e, v1[i].z, o[6]); o[7] = fmaf(e, v1[i].w, o[7]);
+      }
+    }
+    // merge the 4 key groups of the warp (same `sub`, different `grp`)
+    l += __shfl_xor_sync(0xffffffffu, l, 8);
+    l += __shfl_xor_sync(0xffffffffu, l, 16);
 #pragma unroll
-    for (int w = 0; w < NW; ++w) {
-      const float f = (s_m[w] > -INFINITY) ? expf(s_m[w] - M) : 0.f;
-      L = fmaf(f, s_l[w], L);
-      O = fmaf(f, s_o[w][tid], O);
+    for (int j = 0; j < 8; ++j) {
+      o[j] += __shfl_xor_sync(0xffffffffu, o[j], 8);
+      o[j] += __shfl_xor_sync(0xffffffffu, o[j], 16);
+    }
+    __syncthreads();  // previous chunk's merge has finished reading s_o / s_m / s_l
+    if (lane < 8) {
+      *reinterpret_cast<float4*>(&s_o[warp][lane * 8]) = make_float4(o[0], o[1], o[2], o[3]);
+      *reinterpret_cast<float4*>(&s_o[warp][lane * 8 + 4]) = make_float4(o[4], o[5], o[6], o[7]);
+      if (lane == 0) { s_m[warp] = m; s_l[warp] = l; }
+    }
+    __syncthreads();
+    // ---- merge the warps of this chunk into the CTA's running state
+    if (tid < HD) {
+      float cm = M;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) cm = fmaxf(cm, s_m[w]);
+      const float fo = (M > -INFINITY) ? expf(M - cm) : 0.f;
+      L *= fo; O *= fo;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) {
+        const float f = (s_m[w] > -INFINITY) ? expf(s_m[w] - cm) : 0.f;
+        L = fmaf(f, s_l[w], L);
+        O = fmaf(f, s_o[w][tid], O);
+      }
+      M = cm;
     }
   }
   if (nsplit == 1) {
-    if (tid < HD) outp[tid] = O / L;
+    if (tid < HD) store_out(O / L);
     return;
   }
   float* part = p.part + (((size_t)b * p.Hq + h) * p.nsplit_max + split) * (HD + 2);
@@ -467,7 +500,7 @@ __global__ void __launch_bounds__(ATT_THREADS) k_attn(const AttnP p) {
     GL = fmaf(w, __ldcg(pb + s * (HD + 2) + HD + 1), GL);
     if (tid < HD) GO = fmaf(w, __ldcg(pb + s * (HD + 2) + tid), GO);
   }
-  if (tid < HD) outp[tid] = GO / GL;
+  if (tid < HD) store_out(GO / GL);
   if (tid == 0) p.counter[b * p.Hq + h] = 0;
 }
 #endif  // CTB_GPT_KERNELS_IMPL

@@ -28,3 +28,24 @@ for r in range(reps):
     torch.cuda.synchronize()
     dt = time.time() - t
     print(f"B={B} rep {r}: {dt*1e3:.1f} ms  {dt*1e6/(tokens+15):.1f} us/step  ids[0,-1]={ids_out[0,-1].tolist()}", flush=True)
+
+if os.environ.get("CTB_KERNEL_US"):
+    import ctypes as C
+
+    from chattts_b200 import _lib
+
+    lib = _lib.load()
+    sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    out = {}
+    for kind, name in ((0, "qkv"), (1, "attn"), (2, "oproj"), (3, "gateup"), (4, "down"), (5, "heads"), (6, "sample")):
+        for _ in range(2):
+            _lib.check(lib.ctb_gpt_profile_kernel(gpt._handle, kind, sp))
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            _lib.check(lib.ctb_gpt_profile_kernel(gpt._handle, kind, sp))
+        e1.record()
+        torch.cuda.synchronize()
+        out[name] = round(e0.elapsed_time(e1) * 1e3 / (10 * (20 if kind < 5 else 1)), 2)
+    print(f"B={B} kernel_us {out}  layer_sum={sum(v for k, v in out.items() if k not in ('heads', 'sample')):.1f}", flush=True)
