@@ -8,6 +8,7 @@
 #define CTB_GPT_KERNELS_IMPL
 #include "gpt_kernels.cuh"
 #include "tc_decode.cuh"
+#include "mega.cuh"
 
 namespace ctb {
 
@@ -60,6 +61,10 @@ struct ctb_gpt {
   // ---- tensor-core decode path (tc_decode.cuh)
   bool use_tc, tc_ready;
   int tc_min_batch;
+  bool mega_ok;      // one-kernel decode step (mega.cuh), built for B <= 8
+  int mega_max_batch; // batches that use it (default 1: measured faster only there; CTB_MEGA_MAX_BATCH overrides)
+  unsigned* bar;     // its grid-barrier counter
+  unsigned long long* trace;  // CTB_MEGA_TRACE=1: per-phase timestamps of the last step
   float *tc_wqkv, *tc_wgu, *tc_heads_code, *tc_heads_text;  // permuted / norm-folded weight copies
   float *x_hi, *x_lo, *attn_hi, *attn_lo, *h_hi, *h_lo;      // [32][K] tf32-split activations
   CUtensorMap *m_wqkv, *m_wo, *m_wgu, *m_wd;                 // [layers] host arrays
@@ -253,12 +258,17 @@ extern "C" int ctb_gpt_create(const ctb_gpt_config* c, const float* weights_dev,
   TRY(dalloc(&h->active, Bp));
   TRY(dalloc(&h->finish, Bp));
   TRY(dalloc(&h->st, 1));
+  TRY(dalloc(&h->bar, 4));
+  if (getenv("CTB_MEGA_TRACE")) TRY(dalloc(&h->trace, 256));
 #undef TRY
   // static page assignment: row b owns pages [b*ppr, (b+1)*ppr); kernels only see the table
   std::vector<int> bt_host((size_t)c->max_batch * h->pages_per_row);
   for (size_t i = 0; i < bt_host.size(); ++i) bt_host[i] = (int)i;
   cudaMemcpy(h->block_table, bt_host.data(), bt_host.size() * sizeof(int), cudaMemcpyHostToDevice);
   h->use_graph = getenv("CTB_NO_GRAPH") == nullptr;
+  h->mega_ok = getenv("CTB_NO_MEGA") == nullptr && g_num_sms >= 128 && c->intermediate_size == 4 * KC &&
+               (c->hidden_size / 2 + g_num_sms - 1) / g_num_sms <= MG_DOWN_PAIRS;
+  h->mega_max_batch = getenv("CTB_MEGA_MAX_BATCH") ? std::min(8, atoi(getenv("CTB_MEGA_MAX_BATCH"))) : 1;
   // tensor-core decode GEMMs (tc_decode.cuh): CTB_GPT_TC=1 forces them for every batch, CTB_GPT_FMA=1 disables
   // them; by default they serve batches > 16 rows, where the fp32 FMA path turns compute-bound.
   h->tc_ready = getenv("CTB_GPT_FMA") == nullptr && c->max_batch <= 32 &&
@@ -275,7 +285,7 @@ extern "C" int ctb_gpt_destroy(ctb_gpt* h) {
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   void* ptrs[] = {h->x, h->qbuf, h->attn, h->mlp, h->logits, h->kv, h->part, h->block_table, h->seq_len,
                   h->pos, h->counter, h->end_idx, h->idx, h->active, h->finish, h->st, h->tc_wqkv, h->tc_wgu,
-                  h->tc_heads_code, h->tc_heads_text, h->x_hi, h->x_lo, h->attn_hi, h->attn_lo, h->h_hi, h->h_lo};
+                  h->tc_heads_code, h->tc_heads_text, h->x_hi, h->x_lo, h->attn_hi, h->attn_lo, h->h_hi, h->h_lo, h->bar, h->trace};
   delete[] h->m_wqkv; delete[] h->m_wo; delete[] h->m_wgu; delete[] h->m_wd;
   for (void* p : ptrs) if (p) cudaFree(p);
   delete h;
@@ -480,6 +490,53 @@ static int launch_heads_tc(ctb_gpt* h, cudaStream_t s) {
   return launch_tc<DE_HEADS, CS_HEADS>(npad, h->infer_text ? h->m_htext : h->m_hcode, h->m_x[n][0], h->m_x[n][1], p, s);
 }
 
+template <int BT>
+static int launch_step_mega_t(const MegaP& mp, cudaStream_t s) {
+  const size_t smem = (size_t)BT * 4 * KC * sizeof(float);  // [BT][3072] for the down phase
+  static bool attr_done = false;
+  if (!attr_done) {
+    CTB_CUDA(cudaFuncSetAttribute(k_step<BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(g_num_sms); cfg.blockDim = dim3(MG_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;  // every CTA must be resident: the phases meet at grid barriers
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  CTB_CUDA(cudaLaunchKernelEx(&cfg, k_step<BT>, mp));
+  CTB_LAUNCH_CHECK();
+  return CTB_OK;
+}
+
+static int launch_step_mega(ctb_gpt* h, int col, bool sample, cudaStream_t s) {
+  const ctb_gpt_config& c = h->cfg;
+  const ctb_gpt_layout& L = h->lay;
+  MegaP m{};
+  m.W = h->W; m.layer0 = L.layer0; m.layer_stride = L.layer_stride; m.o_wqkv = L.wqkv; m.o_wo = L.wo; m.o_wgu = L.wgate_up;
+  m.o_wd = L.wdown; m.o_ln1 = L.ln1; m.o_ln2 = L.ln2; m.o_final_norm = L.final_norm;
+  m.o_head = h->infer_text ? L.head_text : L.head_code; m.o_emb_code = L.emb_code; m.o_emb_text = L.emb_text;
+  m.o_cos = L.rope_cos; m.o_sin = L.rope_sin;
+  m.L = c.num_layers; m.d = c.hidden_size; m.I = c.intermediate_size; m.Hq = c.num_heads; m.Hkv = c.num_kv_heads;
+  m.hd = c.head_dim; m.eps = c.rms_eps; m.scaling = 1.0f / sqrtf((float)c.head_dim);
+  m.x = h->x; m.qbuf = h->qbuf; m.attn = h->attn; m.mlp = h->mlp; m.logits = h->logits; m.kv = h->kv; m.part = h->part;
+  m.kv_layer_floats = h->kv_layer_floats; m.block_table = h->block_table; m.pages_per_row = h->pages_per_row;
+  m.seq_len = h->seq_len; m.counter = h->counter; m.nsplit_max = h->nsplit_max; m.st = h->st; m.bar = h->bar;
+  m.decode = col < 0; m.col = col < 0 ? 0 : col; m.T0 = h->T0; m.sample = sample ? 1 : 0;
+  m.emb = h->emb; m.mask = h->mask; m.ids_out = h->ids_out; m.max_new = h->max_new; m.num_vq = c.num_vq;
+  m.num_audio = c.num_audio_tokens; m.infer_text = h->infer_text; m.B = h->B;
+  m.hidden_out = h->hiddens_out; m.hidden_stride = h->max_new * c.hidden_size;
+  m.rows_per_item = h->infer_text ? 1 : c.num_vq; m.V = h->infer_text ? c.num_text_tokens : c.num_audio_tokens;
+  m.trace = h->trace;
+  CTB_CUDA(cudaMemsetAsync(h->bar, 0, sizeof(unsigned), s));
+  switch (bt_for(h->B)) {
+    case 1: return launch_step_mega_t<1>(m, s);
+    case 2: return launch_step_mega_t<2>(m, s);
+    case 4: return launch_step_mega_t<4>(m, s);
+    default: return launch_step_mega_t<8>(m, s);
+  }
+}
+
 // One loop iteration.  col >= 0: prefill column `col` of the prompt; col < 0: decode step.
 // sample: run heads + sampler + finalize (last prompt column and every decode step).
 static int enqueue_step(ctb_gpt* h, int col, bool sample, cudaStream_t s) {
@@ -487,6 +544,21 @@ static int enqueue_step(ctb_gpt* h, int col, bool sample, cudaStream_t s) {
   const ctb_gpt_layout& L = h->lay;
   const int decode = col < 0;
   int rc;
+
+  if (h->mega_ok && !h->use_tc && h->B <= h->mega_max_batch) {
+    // small batches: the whole step (input -> 20 layers -> heads) is one persistent cooperative kernel
+    if ((rc = launch_step_mega(h, col, sample, s))) return rc;
+    if (!sample) return CTB_OK;
+    const StepCtx xm = make_ctx(h, decode);
+    if ((rc = launch_sampler(h, xm, s))) return rc;
+    FinalP fm{};
+    fm.st = h->st; fm.B = h->B; fm.rows_per_item = h->infer_text ? 1 : c.num_vq; fm.num_vq = c.num_vq;
+    fm.max_new = h->max_new; fm.eos = h->sampler.eos_token; fm.idx = h->idx; fm.ids_out = h->ids_out;
+    fm.finish = h->finish; fm.end_idx = h->end_idx;
+    CTB_CUDA(launch_pdl(k_finalize, dim3(1), dim3(256), 0, s, fm));
+    CTB_LAUNCH_CHECK();
+    return CTB_OK;
+  }
 
   InputP ip{};
   ip.st = h->st; ip.decode = decode; ip.B = h->B; ip.d = c.hidden_size; ip.col = decode ? 0 : col; ip.T0 = h->T0;
@@ -595,6 +667,12 @@ extern "C" int ctb_gpt_decode(ctb_gpt* h, int32_t n_steps, void* stream) {
       return rc;
     }
   }
+  return CTB_OK;
+}
+
+extern "C" int ctb_gpt_debug_trace(ctb_gpt* h, unsigned long long* host_out, int n) {
+  if (!h || !h->trace) return set_err(CTB_ERR_STATE, "trace disabled (set CTB_MEGA_TRACE=1 before ctb_gpt_create)");
+  CTB_CUDA(cudaMemcpy(host_out, h->trace, sizeof(unsigned long long) * (size_t)std::min(n, 256), cudaMemcpyDeviceToHost));
   return CTB_OK;
 }
 

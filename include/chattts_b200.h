@@ -138,6 +138,10 @@ int ctb_gpt_status_query(ctb_gpt* h, ctb_gpt_status* out, int32_t* end_idx_host,
  * 5 = heads, 6 = sampler: one launch).  No reference counterpart. */
 int ctb_gpt_profile_kernel(ctb_gpt* h, int32_t kind, void* stream);
 
+/* Profiling aid: with CTB_MEGA_TRACE=1 in the environment at ctb_gpt_create, the one-kernel decode step records
+ * a %globaltimer stamp (ns) of CTA 0 after every grid barrier of the most recent step; copies up to n of them. */
+int ctb_gpt_debug_trace(ctb_gpt* h, unsigned long long* host_out, int n);
+
 /* Stand-alone sampling tail over caller-provided logits (minimum slice of SURVEY.md 7.2;
  * same kernel the decode loop uses).
  *   logits_dev [rows, V] fp32 (not modified); gen_ids_dev [rows/rpi, gen_stride, rpi] int32 with

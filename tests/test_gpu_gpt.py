@@ -140,3 +140,40 @@ def test_streaming_yields_cumulative_chunks():
     assert lens == [24, 48, 60]
     full = _run(gpt, embed, [16], 1, 1234, 60)[-1]
     assert torch.equal(outs[-1].ids[0], full.ids[0]) and torch.equal(outs[0].ids[0], full.ids[0][:24])
+
+
+@pytest.mark.parametrize("env,lengths", [({"CTB_GPT_TC": "1"}, [5, 12, 9]), ({"CTB_GPT_TC": "1"}, [16]),
+                                         ({"CTB_MEGA_MAX_BATCH": "8"}, [5, 12, 9]), ({"CTB_NO_MEGA": "1"}, [16]),
+                                         ({"CTB_NO_GRAPH": "1", "CTB_NO_PDL": "1"}, [7, 3])])
+def test_every_decode_back_end_gives_the_same_ids(env, lengths):
+    """The three step implementations - PDL-chained FMA kernels, the one-kernel cooperative step (mega.cuh) and the
+    tcgen05 3xTF32 GEMM step (tc_decode.cuh) - are selected by batch size; each is forced here on batches it would
+    not get by default and must reproduce the CPU oracle's ids exactly."""
+    import os
+
+    from chattts_b200.config import Config
+    from chattts_b200.embed import Embed
+    from chattts_b200.gpt import GPT
+    from chattts_b200.synth import synth_embed_state, synth_gpt_state
+
+    gs, es = synth_gpt_state(0), synth_embed_state(1)
+    orc = GPTOracle(gs, es)
+    ids, mask, tmask = synth_prompt_batch(lengths, seed=13)
+    ref = orc.generate(orc.embed_prompt(ids, tmask), ids, torch.tensor([0.3] * 4), 625, attention_mask=mask,
+                       max_new_token=80, min_new_token=80, sampler=SamplerParams(), return_hidden=True, manual_seed=21)
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        embed = Embed(768, 626, 21178, 4).load_state_dict(es).to("cuda")
+        gpt = GPT(Config().gpt, embed, device="cuda", device_gpt="cuda", max_batch=len(lengths), max_context=128)
+        gpt.load_state(gs)
+        out = _run(gpt, embed, lengths, 13, 21, 80)[-1]
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    for b in range(len(lengths)):
+        assert torch.equal(out.ids[b].cpu(), ref.ids[b]), (env, b)
+        assert (out.hiddens[b].cpu() - ref.hiddens[b]).abs().max() < 1e-4

@@ -49,3 +49,22 @@ if os.environ.get("CTB_KERNEL_US"):
         torch.cuda.synchronize()
         out[name] = round(e0.elapsed_time(e1) * 1e3 / (10 * (20 if kind < 5 else 1)), 2)
     print(f"B={B} kernel_us {out}  layer_sum={sum(v for k, v in out.items() if k not in ('heads', 'sample')):.1f}", flush=True)
+
+if os.environ.get("CTB_MEGA_TRACE"):
+    import ctypes as C
+    import numpy as np
+
+    from chattts_b200 import _lib
+
+    buf = np.zeros(128, dtype=np.uint64)
+    _lib.check(_lib.load().ctb_gpt_debug_trace(gpt._handle, buf.ctypes.data_as(C.c_void_p), 128))
+    t = buf[:103].astype(np.int64)
+    d = np.diff(t) / 1e3
+    names = ["qkv", "attn", "oproj", "gateup", "down"]
+    per = {n: [] for n in names}
+    for l in range(20):
+        for j, n in enumerate(names):
+            per[n].append(d[l * 5 + j])
+    print("phase us (median over layers):", {n: round(float(np.median(v)), 2) for n, v in per.items()},
+          "heads", round(float(d[100]), 2), "total", round(float(t[101] - t[0]) / 1e3, 1))
+    print("layer 10:", [round(float(x), 2) for x in d[50:55]])
