@@ -182,14 +182,13 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     if rank != 0:
         return None
 
-    # ---- roofline of the dominant kernel (gate/up GEMV), timed live with CUDA events
+    # ---- roofline of the dominant kernel, timed live with CUDA events on the launching stream
     peak, peak_src = measured_peaks()
     stream_ptr = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     step_resident()
-    kern = {}
-    for kind, name in ((3, "k_gemv<GATEUP>"), (4, "k_gemv<DOWN>"), (0, "k_gemv<QKV>"), (2, "k_gemv<OPROJ>"),
-                       (1, "k_attn"), (5, "k_gemv<HEADS>"), (6, "k_sample")):
-        reps = 20
+    torch.cuda.synchronize()
+
+    def time_kind(kind, reps, per_call):
         for _ in range(3):
             _lib.check(lib.ctb_gpt_profile_kernel(gpt._handle, kind, stream_ptr))
         torch.cuda.synchronize()
@@ -199,20 +198,67 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             _lib.check(lib.ctb_gpt_profile_kernel(gpt._handle, kind, stream_ptr))
         e1.record()
         torch.cuda.synchronize()
-        n_launch = reps * (20 if kind < 5 else 1)
-        kern[name] = e0.elapsed_time(e1) * 1e3 / n_launch  # us per launch
-    gu_bytes = 2 * 3072 * 768 * 4 + B * 768 * 4 + B * 3072 * 4  # weights + x in + mlp out
-    achieved = gu_bytes / (kern["k_gemv<GATEUP>"] * 1e-6) / 1e9
+        return e0.elapsed_time(e1) * 1e3 / (reps * per_call)  # us per launch
+
     t_avg = PROMPT_LEN + tokens / 2
     step_bytes = algorithmic_bytes_per_step(B, t_avg)
     step_us = ms_per_step * 1e3 / (tokens + PROMPT_LEN - 1)
-    roofline = {"bound": "hbm", "kernel": "k_gemv<BT,EPI_GATEUP>", "achieved": round(achieved, 1), "peak": peak,
-                "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
-                "bytes_per_launch": gu_bytes, "us_per_launch": round(kern["k_gemv<GATEUP>"], 3),
-                "kernel_us": {k: round(v, 3) for k, v in kern.items()},
-                "whole_step": {"algorithmic_bytes": int(step_bytes), "us": round(step_us, 2),
-                               "achieved_gbs": round(step_bytes / (step_us * 1e-6) / 1e9, 1),
-                               "frac": round(step_bytes / (step_us * 1e-6) / 1e9 / peak, 4)}}
+    one_kernel = B == 1 and not os.environ.get("CTB_NO_MEGA")
+    kern = {}
+    if one_kernel:
+        # B = 1 runs the whole step as ONE persistent cooperative kernel (k_step: 101 grid-barrier phases)
+        step_resident()  # fresh state: the hook advances the context by one token per call
+        torch.cuda.synchronize()
+        us = time_kind(7, 16, 1)
+        kbytes = algorithmic_bytes_per_step(B, PROMPT_LEN + tokens + 10)
+        achieved = kbytes / (us * 1e-6) / 1e9
+        roofline = {"bound": "hbm", "kernel": "k_step<1> (one launch = the whole decode step: 20 layers + heads, 101 phases)",
+                    "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                    "traffic": None, "peak_source": peak_src, "bytes_per_launch": int(kbytes),
+                    "us_per_launch": round(us, 2)}
+    else:
+        for kind, name in ((3, "gateup"), (4, "down"), (0, "qkv"), (2, "oproj"), (1, "k_attn"), (5, "heads"), (6, "k_sample")):
+            kern[name] = time_kind(kind, 20, 20 if kind < 5 else 1)
+        gu_bytes = 2 * 3072 * 768 * 4 + B * 768 * 4 + B * 3072 * 4  # weights + x in + mlp out
+        achieved = gu_bytes / (kern["gateup"] * 1e-6) / 1e9
+        kname = "k_tc_dec<DE_GATEUP> (tcgen05 3xTF32)" if B > 16 else "k_gemv<BT,EPI_GATEUP>"
+        roofline = {"bound": "hbm", "kernel": kname, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                    "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                    "bytes_per_launch": gu_bytes, "us_per_launch": round(kern["gateup"], 3),
+                    "kernel_us": {k: round(v, 3) for k, v in kern.items()}}
+    roofline["whole_step"] = {"algorithmic_bytes": int(step_bytes), "us": round(step_us, 2),
+                              "achieved_gbs": round(step_bytes / (step_us * 1e-6) / 1e9, 1),
+                              "frac": round(step_bytes / (step_us * 1e-6) / 1e9 / peak, 4)}
+
+    # ---- the metric at the other batch sizes it is quoted on, and hot path 2 (BASELINE configs[3]); short runs
+    sweep = {}
+    if world == 1 and not args.no_sweep:
+        del gpt
+        torch.cuda.empty_cache()
+        for bb in (8, 32):
+            g2 = GPT(cfg.gpt, embed, device=dev, device_gpt=dev, max_batch=bb, max_context=PROMPT_LEN + tokens + 16)
+            g2.load_state(synth_gpt_state(0))
+            i2, m2, tm2, _, sc2, q2 = build_inputs(bb, tokens, seed=1)
+            e2, mk2, qd2 = embed(i2, tm2).to(dev), m2.to(dev).to(torch.uint8), q2.to(dev)
+            o2 = torch.zeros(bb, tokens, 4, dtype=torch.int32, device=dev)
+            for _ in range(2):
+                g2.enqueue_generate(e2, mk2, sc2, qd2, tokens, False, o2, None)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(2):
+                g2.enqueue_generate(e2, mk2, sc2, qd2, tokens, False, o2, None)
+            e1.record()
+            torch.cuda.synchronize()
+            ms2 = e0.elapsed_time(e1) / 2
+            sb = algorithmic_bytes_per_step(bb, t_avg)
+            us2 = ms2 * 1e3 / (tokens + PROMPT_LEN - 1)
+            sweep[f"batch_{bb}"] = {"value": round(bb * tokens / (ms2 / 1e3), 1), "unit": "speech-tokens/s",
+                                    "ms_per_step": round(ms2, 2), "rtf": round((ms2 / 1e3) / (bb * tokens * 512 / 24000.0), 6),
+                                    "step_us": round(us2, 1), "hbm_frac": round(sb / (us2 * 1e-6) / 1e9 / peak, 4)}
+            del g2
+            torch.cuda.empty_cache()
+        sweep["decoder_c4"] = bench_decoder(dev)
 
     cpu = cpu_baseline_sample(B)
     audio_s = B * tokens * 512 / 24000.0
@@ -231,7 +277,38 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                 "rtf": round((ms_e2e / 1e3) / audio_s, 6)},
         "gpu_launches": launches, "clocks": clk.summary(), "roofline": roofline, "cpu_baseline": cpu,
     }
+    if sweep:
+        line["other_configs"] = sweep
     return line
+
+
+def bench_decoder(dev, B: int = 64, T: int = 469):
+    """Hot path 2 at BASELINE configs[3]: DVAE decoder + Vocos + iSTFT of 10 s of hidden states, batch 64."""
+    from chattts_b200.config import Config
+    from chattts_b200.decoder import DVAE, Vocos
+    from chattts_b200.synth import synth_dvae_state, synth_vocos_state
+
+    cfg = Config()
+    voc = Vocos(cfg.vocos, dev, max_batch=B, max_tokens=T)
+    voc.state = synth_vocos_state(5)
+    dec = DVAE(cfg.decoder, dim=cfg.decoder.idim, device=dev, vocos=voc, max_batch=B, max_tokens=T)
+    dec.load_state_dict(synth_dvae_state(2, cfg.decoder, cfg.decoder.idim))
+    x = torch.randn(B, T, 768, generator=torch.Generator().manual_seed(1)).to(dev)
+    for _ in range(2):
+        wav = dec.engine.tokens_to_wav(x, 1)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        wav = dec.engine.tokens_to_wav(x, 1)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 3
+    frames = B * 2 * T
+    flops = frames * 78.7e6  # SURVEY.md 8d: 78.7 MFLOP per mel frame on the hidden path
+    return {"workload": f"DVAE decoder + Vocos + iSTFT, batch {B} x {T} tokens (10 s each), hidden path, tcgen05 3xTF32 GEMMs",
+            "ms": round(ms, 2), "audio_samples_per_s": round(wav.numel() / (ms / 1e3), 1),
+            "rtf": round((ms / 1e3) / (wav.numel() / 24000.0), 7), "tflops_fp32_equiv": round(flops / (ms / 1e3) / 1e12, 1)}
 
 
 def cpu_baseline_sample(B: int, budget_s: float = 15.0):
@@ -317,6 +394,7 @@ def main():
     ap.add_argument("--tokens", type=int, default=512)
     ap.add_argument("--ref-tokens", type=int, default=48)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-sweep", action="store_true", help="skip the short batch-8/32 and decoder side measurements")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
 

@@ -57,6 +57,7 @@ struct ctb_gpt {
   int32_t* ids_out;
   float* hiddens_out;
   cudaGraphExec_t graph_exec;
+  uint64_t graph_kernels;  // kernel nodes captured in graph_exec
   cudaStream_t cap_stream;
   // ---- tensor-core decode path (tc_decode.cuh)
   bool use_tc, tc_ready;
@@ -601,6 +602,10 @@ extern "C" int ctb_gpt_profile_kernel(ctb_gpt* h, int32_t kind, void* stream) {
   int rc;
   if (kind == 5) return h->use_tc ? launch_heads_tc(h, s) : launch_heads(h, x, s);
   if (kind == 6) return launch_sampler(h, x, s);
+  if (kind == 7) {  // the one-kernel decode step alone (context grows by one token per call)
+    if (!(h->mega_ok && h->B <= 8)) return set_err(CTB_ERR_STATE, "one-kernel step unavailable for this handle/batch");
+    return launch_step_mega(h, -1, true, s);
+  }
   for (int l = 0; l < h->cfg.num_layers; ++l)
     if ((rc = (h->use_tc && kind != 1) ? launch_layer_kernel_tc(h, l, kind, s) : launch_layer_kernel(h, x, l, kind, s)))
       return rc;
@@ -652,7 +657,10 @@ extern "C" int ctb_gpt_decode(ctb_gpt* h, int32_t n_steps, void* stream) {
     cudaGraph_t graph;
     if (!h->cap_stream) CTB_CUDA(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
     CTB_CUDA(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
+    const uint64_t before = g_launches.load();
     rc = enqueue_step(h, -1, true, h->cap_stream);
+    h->graph_kernels = g_launches.load() - before;
+    g_launches.store(before);  // captured, not launched
     cudaError_t e = cudaStreamEndCapture(h->cap_stream, &graph);
     if (rc) return rc;
     if (e != cudaSuccess) return set_err(CTB_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
@@ -662,7 +670,7 @@ extern "C" int ctb_gpt_decode(ctb_gpt* h, int32_t n_steps, void* stream) {
   for (int i = 0; i < n_steps; ++i) {
     if (h->graph_exec) {
       CTB_CUDA(cudaGraphLaunch(h->graph_exec, s));
-      g_launches.fetch_add(5 * h->cfg.num_layers + 4, std::memory_order_relaxed);
+      g_launches.fetch_add(h->graph_kernels, std::memory_order_relaxed);
     } else if ((rc = enqueue_step(h, -1, true, s))) {
       return rc;
     }
