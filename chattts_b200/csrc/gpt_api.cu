@@ -493,7 +493,8 @@ static int launch_heads_tc(ctb_gpt* h, cudaStream_t s) {
 
 template <int BT>
 static int launch_step_mega_t(const MegaP& mp, cudaStream_t s) {
-  const size_t smem = (size_t)BT * 4 * KC * sizeof(float);  // [BT][3072] for the down phase
+  // [BT][3072] activations (down phase) + for BT <= 2 the gate/up weight landing zone
+  const size_t smem = (size_t)BT * 4 * KC * sizeof(float) + (BT <= 2 ? (size_t)MG_GW_FLOATS * sizeof(float) : 0);
   static bool attr_done = false;
   if (!attr_done) {
     CTB_CUDA(cudaFuncSetAttribute(k_step<BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

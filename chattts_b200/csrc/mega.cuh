@@ -46,12 +46,18 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch) {
+// Split in two so that the next phase's weight prefetch is issued BETWEEN arrive and wait: a release must not have
+// to wait for those (long) loads, and they stream while the CTA waits for the others.
+__device__ __forceinline__ void grid_arrive(unsigned* counter, unsigned& epoch) {
   __syncthreads();
   if (threadIdx.x == 0) {
     epoch += gridDim.x;
     // release: this CTA's global writes (ordered before by bar.sync) become visible with the arrival
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+  }
+}
+__device__ __forceinline__ void grid_wait(unsigned* counter, unsigned& epoch) {
+  if (threadIdx.x == 0) {
     while (ld_acquire_u32(counter) < epoch) {}
   }
   __syncthreads();
@@ -65,6 +71,9 @@ struct MegaCtx {
   float* rinv;     // [BT]
   int* pos;        // [BT]
   int* active;     // [BT]
+  const float* cos_s;  // [BT][64] RoPE rows of this step's positions (shared memory)
+  const float* sin_s;
+  const int* page;     // [BT] KV page of this step's position
 };
 
 // rows of a 2-row warp task (same mapping as k_gemv)
@@ -96,12 +105,8 @@ __device__ __forceinline__ void mg_load_w(const MegaP& p, const float* Wm, int t
   for (int i = 0; i < 6; ++i) { w0[i] = ldg_stream(w0p + i * 32); w1[i] = ldg_stream(w1p + i * 32); }
 }
 
-// K = 768 phase: stage activations (+ optional RMSNorm) and stream this CTA's row tasks.  `pre0/pre1` hold the
-// first task's weights, requested before the preceding grid barrier.
 template <int BT, int EPI>
-__device__ __forceinline__ void mg_gemv_phase(const MegaP& p, const MegaCtx<BT>& c, const float* Wm, int ntasks, int nrows,
-                                              const float* xin, const float* normw, float* kvl, float4 (&w0)[6],
-                                              float4 (&w1)[6], bool staged) {
+__device__ __forceinline__ void mg_stage(const MegaP& p, const MegaCtx<BT>& c, const float* xin, const float* normw, bool staged) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nb = p.B;
   if (!staged) {
@@ -135,6 +140,17 @@ __device__ __forceinline__ void mg_gemv_phase(const MegaP& p, const MegaCtx<BT>&
       }
     }
   }
+}
+
+// K = 768 phase: stage activations (+ optional RMSNorm) and stream this CTA's row tasks.  `pre0/pre1` hold the
+// first task's weights, requested before the preceding grid barrier.
+template <int BT, int EPI>
+__device__ __forceinline__ void mg_gemv_phase(const MegaP& p, const MegaCtx<BT>& c, const float* Wm, int ntasks, int nrows,
+                                              const float* xin, const float* normw, float* kvl, float4 (&w0)[6],
+                                              float4 (&w1)[6], bool staged, float rx0 = 0.f, float rx1 = 0.f) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nb = p.B;
+  mg_stage<BT, EPI>(p, c, xin, normw, staged);
   constexpr int LPB = 32 / BT;
   const int tstride = gridDim.x * MG_WARPS;
   for (int task = blockIdx.x * MG_WARPS + warp; task < ntasks; task += tstride) {
@@ -177,22 +193,22 @@ __device__ __forceinline__ void mg_gemv_phase(const MegaP& p, const MegaCtx<BT>&
       const int pos = c.pos[b];
       float o0 = v0, o1 = v1;
       if (which < 2) {
-        const float* cs = p.W + p.o_cos + (size_t)pos * p.hd;
-        const float* sn = p.W + p.o_sin + (size_t)pos * p.hd;
-        o0 = __fadd_rn(__fmul_rn(v0, __ldg(cs + j)), __fmul_rn(-v1, __ldg(sn + j)));
-        o1 = __fadd_rn(__fmul_rn(v1, __ldg(cs + j + half)), __fmul_rn(v0, __ldg(sn + j + half)));
+        const float* cs = c.cos_s + b * 64;
+        const float* sn = c.sin_s + b * 64;
+        o0 = __fadd_rn(__fmul_rn(v0, cs[j]), __fmul_rn(-v1, sn[j]));
+        o1 = __fadd_rn(__fmul_rn(v1, cs[j + half]), __fmul_rn(v0, sn[j + half]));
       }
       if (which == 0) {
         p.qbuf[(size_t)b * p.Hq * p.hd + h * p.hd + j] = o0;
         p.qbuf[(size_t)b * p.Hq * p.hd + h * p.hd + j + half] = o1;
       } else {
-        const int page = __ldg(p.block_table + b * p.pages_per_row + pos / kPageTokens);
-        float* dst = kvl + kv_off(page, which - 1, h, pos % kPageTokens, p.Hkv, p.hd);
+        float* dst = kvl + kv_off(c.page[b], which - 1, h, pos % kPageTokens, p.Hkv, p.hd);
         dst[j] = o0; dst[j + half] = o1;
       }
     } else if (EPI == MG_OPROJ) {
-      p.x[(size_t)b * p.d + r0] = __fadd_rn(ldg_cg(&p.x[(size_t)b * p.d + r0]), v0);
-      if (2 * task + 1 < nrows) p.x[(size_t)b * p.d + r0 + 1] = __fadd_rn(ldg_cg(&p.x[(size_t)b * p.d + r0 + 1]), v1);
+      // one task per warp (384 tasks <= grid * 8): the residual values were requested before the grid barrier
+      p.x[(size_t)b * p.d + r0] = __fadd_rn(rx0, v0);
+      if (2 * task + 1 < nrows) p.x[(size_t)b * p.d + r0 + 1] = __fadd_rn(rx1, v1);
     } else if (EPI == MG_GATEUP) {
       const float sg = __fdiv_rn(v0, __fadd_rn(1.0f, expf(-v0)));
       p.mlp[(size_t)b * p.I + task] = __fmul_rn(sg, v1);
@@ -207,8 +223,71 @@ __device__ __forceinline__ void mg_gemv_phase(const MegaP& p, const MegaCtx<BT>&
   }
 }
 
-// attention phase: units (b, h, s) strided over the grid; unit s walks key chunks s, s + S, ... with a running softmax
+// gate/up for BT <= 2: all (<= 3) tasks of the warp were requested before the barrier (144 registers), so the phase
+// exposes no DRAM round trip at all.
+constexpr int MG_GU_TASKS = 3;
+constexpr int MG_SMAX = 12;  // max attention splits per (row, head) when the O-proj phase merges them (BT <= 2)
+// Shared-memory landing zone for the warp's gate/up weights: [warp][task][row][192 float4] (18 KiB per warp).
+// cp.async needs no registers, so all 36 x 16 B requests per lane are in flight while the CTA waits at the barrier.
+constexpr int MG_GW_FLOATS = MG_WARPS * MG_GU_TASKS * 2 * KC;
 template <int BT>
+__device__ __forceinline__ void mg_gateup_load(const MegaP& p, const float* Wm, int lane, int warp, float* gws) {
+  const int tstride = gridDim.x * MG_WARPS;
+#pragma unroll
+  for (int j = 0; j < MG_GU_TASKS; ++j) {
+    const int task = blockIdx.x * MG_WARPS + warp + j * tstride;
+    if (task < p.I) {
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const float* src = Wm + (size_t)(r ? p.I + task : task) * KC;
+        float* dst = gws + ((size_t)(warp * MG_GU_TASKS + j) * 2 + r) * KC;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) cp_async16(dst + (i * 32 + lane) * 4, src + (i * 32 + lane) * 4);
+      }
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+template <int BT>
+__device__ __forceinline__ void mg_gateup_small(const MegaP& p, const MegaCtx<BT>& c, const float* normw, const float* gws) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  mg_stage<BT, MG_GATEUP>(p, c, p.x, normw, false);  // its cp.async wait also covers the weight group
+  __syncwarp();
+  constexpr int LPB = 32 / BT;
+  const int tstride = gridDim.x * MG_WARPS;
+#pragma unroll
+  for (int j = 0; j < MG_GU_TASKS; ++j) {
+    const int task = blockIdx.x * MG_WARPS + warp + j * tstride;
+    if (task >= p.I) break;
+    const float4* g0 = reinterpret_cast<const float4*>(gws + ((size_t)(warp * MG_GU_TASKS + j) * 2) * KC);
+    const float4* g1 = g0 + KC / 4;
+    float acc0[BT], acc1[BT];
+#pragma unroll
+    for (int b = 0; b < BT; ++b) { acc0[b] = 0.f; acc1[b] = 0.f; }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const float4 a = g0[i * 32 + lane], bq = g1[i * 32 + lane];
+#pragma unroll
+      for (int b = 0; b < BT; ++b) {
+        const float4 xv = reinterpret_cast<const float4*>(c.xs)[b * (KC / 4) + i * 32 + lane];
+        acc0[b] = fmaf(a.x, xv.x, acc0[b]); acc0[b] = fmaf(a.y, xv.y, acc0[b]);
+        acc0[b] = fmaf(a.z, xv.z, acc0[b]); acc0[b] = fmaf(a.w, xv.w, acc0[b]);
+        acc1[b] = fmaf(bq.x, xv.x, acc1[b]); acc1[b] = fmaf(bq.y, xv.y, acc1[b]);
+        acc1[b] = fmaf(bq.z, xv.z, acc1[b]); acc1[b] = fmaf(bq.w, xv.w, acc1[b]);
+      }
+    }
+    warp_reduce_scatter<BT>(acc0);
+    warp_reduce_scatter<BT>(acc1);
+    if ((lane % LPB) == 0 && (lane / LPB) < p.B) {
+      const float v0 = acc0[0], v1 = acc1[0];
+      const float sg = __fdiv_rn(v0, __fadd_rn(1.0f, expf(-v0)));
+      p.mlp[(size_t)(lane / LPB) * p.I + task] = __fmul_rn(sg, v1);
+    }
+  }
+}
+
+// attention phase: units (b, h, s) strided over the grid; unit s walks key chunks s, s + S, ... with a running softmax
+template <int BT, bool DEFER>
 __device__ __forceinline__ void mg_attn_phase(const MegaP& p, const MegaCtx<BT>& c, const float* kvl, int S) {
   constexpr int HD = 64, NW = MG_WARPS, CH = ATT_CHUNK, PER_WARP = CH / NW, ITER = PER_WARP / 4;
   static_assert(ITER >= 1, "attention chunk too small for the warp count");
@@ -222,7 +301,7 @@ __device__ __forceinline__ void mg_attn_phase(const MegaP& p, const MegaCtx<BT>&
     const int split = u % S, h = (u / S) % p.Hq, b = u / (S * p.Hq);
     float* outp = p.attn + (size_t)b * p.Hq * HD + h * HD;
     __syncthreads();  // shared state of the previous unit is no longer read
-    if (!c.active[b]) { if (split == 0 && tid < HD) outp[tid] = 0.f; continue; }
+    if (!c.active[b]) { if (!DEFER && split == 0 && tid < HD) outp[tid] = 0.f; continue; }
     const int n = c.pos[b] + 1;
     const int nchunk = (n + CH - 1) / CH;
     const int nsplit = min(nchunk, S);
@@ -303,13 +382,14 @@ __device__ __forceinline__ void mg_attn_phase(const MegaP& p, const MegaCtx<BT>&
         M = cm;
       }
     }
-    if (nsplit == 1) {
+    if (!DEFER && nsplit == 1) {
       if (tid < HD) outp[tid] = O / L;
       continue;
     }
     float* part = p.part + (((size_t)b * p.Hq + h) * p.nsplit_max + split) * (HD + 2);
     if (tid < HD) part[tid] = O;
     if (tid == 0) { part[HD] = M; part[HD + 1] = L; }
+    if (DEFER) continue;  // the O-proj phase merges the splits while it stages its input (mg_attn_merge)
     __threadfence();
     __syncthreads();
     if (tid == 0) s_last = (atomicAdd(&p.counter[b * p.Hq + h], 1) == nsplit - 1);
@@ -328,6 +408,45 @@ __device__ __forceinline__ void mg_attn_phase(const MegaP& p, const MegaCtx<BT>&
     if (tid < HD) outp[tid] = GO / GL;
     if (tid == 0) p.counter[b * p.Hq + h] = 0;
   }
+}
+
+// BT <= 2: merge the flash-decoding partials of every (row, head) straight into the O-proj staging buffer xs[b][h*64+d]
+// (each CTA redundantly; 12 x S x 66 floats per row from L2) - no atomics / fences / last-CTA pass in the attention phase.
+template <int BT>
+__device__ __forceinline__ void mg_attn_merge(const MegaP& p, const MegaCtx<BT>& c, int S, float* scratch) {
+  constexpr int HD = 64, PW = HD + 2;
+  // 1) bulk-copy the live partials [b][h][s < S][66] into shared memory (one L2 round trip, no registers)
+  const int per_row = p.Hq * S * PW;  // floats; PW even and bases 8-byte aligned -> 8-byte cp.async
+  for (int i = threadIdx.x; i < p.B * per_row / 2; i += MG_THREADS) {
+    const int b = i / (per_row / 2), r = i % (per_row / 2);
+    const int h = r / (S * PW / 2), q = r % (S * PW / 2);
+    const float* src = p.part + (((size_t)b * p.Hq + h) * p.nsplit_max) * PW + 2 * q;
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(scratch + (size_t)b * per_row + 2 * r);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
+  }
+  cp_async_wait_all();
+  __syncthreads();
+  // 2) merge from shared memory into the O-proj staging buffer xs[b][h*64 + d]
+  for (int i = threadIdx.x; i < BT * KC; i += MG_THREADS) {
+    const int b = i / KC, col = i % KC, h = col / HD, d = col % HD;
+    float v = 0.f;
+    if (b < p.B && c.active[b]) {
+      const int n = c.pos[b] + 1;
+      const int nsplit = min((n + ATT_CHUNK - 1) / ATT_CHUNK, S);
+      const float* pb = scratch + (size_t)b * per_row + (size_t)h * S * PW;
+      float GM = -INFINITY;
+      for (int s = 0; s < nsplit; ++s) GM = fmaxf(GM, pb[s * PW + HD]);
+      float GL = 0.f, GO = 0.f;
+      for (int s = 0; s < nsplit; ++s) {
+        const float w = expf(pb[s * PW + HD] - GM);
+        GL = fmaf(w, pb[s * PW + HD + 1], GL);
+        GO = fmaf(w, pb[s * PW + d], GO);
+      }
+      v = GO / GL;
+    }
+    c.xs[i] = v;
+  }
+  __syncthreads();
 }
 
 // down projection (K = 3072): the CTA's 8 warps split K (384 each) for the CTA's row pairs; partials meet in
@@ -350,7 +469,7 @@ __device__ __forceinline__ void mg_down_load(const MegaP& p, const float* Wd, in
 }
 
 template <int BT>
-__device__ __forceinline__ void mg_down_phase(const MegaP& p, const MegaCtx<BT>& c, float4 (&dw)[MG_DOWN_PAIRS][2][3]) {
+__device__ __forceinline__ void mg_down_phase(const MegaP& p, const MegaCtx<BT>& c, float4 (&dw)[MG_DOWN_PAIRS][2][3], float rx) {
   __shared__ float red[MG_DOWN_PAIRS][MG_WARPS][2][BT];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nb = p.B, npairs = p.d / 2, I4 = p.I / 4;
@@ -388,15 +507,16 @@ __device__ __forceinline__ void mg_down_phase(const MegaP& p, const MegaCtx<BT>&
   }
   __syncthreads();
   // final: thread -> (pair j, row r, batch b); K slices summed in the order 0..7 (deterministic)
-  for (int i = tid; i < MG_DOWN_PAIRS * 2 * BT; i += MG_THREADS) {
-    const int b = i % BT, r = (i / BT) % 2, j = i / (2 * BT);
+  static_assert(MG_DOWN_PAIRS * 2 * BT <= MG_THREADS, "one final-reduce element per thread");
+  if (tid < MG_DOWN_PAIRS * 2 * BT) {
+    const int b = tid % BT, r = (tid / BT) % 2, j = tid / (2 * BT);
     const int pair = blockIdx.x + j * gridDim.x;
-    if (pair >= npairs || b >= nb) continue;
-    float v = red[j][0][r][b];
+    if (pair < npairs && b < nb) {
+      float v = red[j][0][r][b];
 #pragma unroll
-    for (int w = 1; w < MG_WARPS; ++w) v = __fadd_rn(v, red[j][w][r][b]);
-    float* xr = p.x + (size_t)b * p.d + 2 * pair + r;
-    *xr = __fadd_rn(ldg_cg(xr), v);
+      for (int w = 1; w < MG_WARPS; ++w) v = __fadd_rn(v, red[j][w][r][b]);
+      p.x[(size_t)b * p.d + 2 * pair + r] = __fadd_rn(rx, v);  // rx: residual requested before the barrier
+    }
   }
 }
 
@@ -404,8 +524,10 @@ template <int BT>
 __global__ void __launch_bounds__(MG_THREADS, 1) k_step(const MegaP p) {
   extern __shared__ __align__(16) float mg_smem[];
   __shared__ float s_rinv[BT];
-  __shared__ int s_pos[BT], s_active[BT];
-  MegaCtx<BT> c{mg_smem, s_rinv, s_pos, s_active};
+  __shared__ int s_pos[BT], s_active[BT], s_page[BT];
+  __shared__ float s_cos[BT * 64], s_sin[BT * 64];
+  MegaCtx<BT> c{mg_smem, s_rinv, s_pos, s_active, s_cos, s_sin, s_page};
+  float* gws = mg_smem + BT * 4 * KC;  // BT <= 2 only: gate/up weight landing zone behind the activation buffer
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   pdl_trigger();
   const float* W0 = p.W + p.layer0;
@@ -430,8 +552,14 @@ __global__ void __launch_bounds__(MG_THREADS, 1) k_step(const MegaP p) {
       act = p.decode ? 1 : (p.mask[(size_t)tid * p.T0 + p.col] != 0);
     }
     s_pos[tid] = pos; s_active[tid] = act;
+    s_page[tid] = tid < p.B ? __ldg(p.block_table + tid * p.pages_per_row + pos / kPageTokens) : 0;
   }
   __syncthreads();
+  for (int i = tid; i < BT * 64; i += MG_THREADS) {  // RoPE rows of this step's positions (p.hd == 64)
+    const int b = i / 64;
+    s_cos[i] = b < p.B ? __ldg(p.W + p.o_cos + (size_t)s_pos[b] * 64 + (i % 64)) : 0.f;
+    s_sin[i] = b < p.B ? __ldg(p.W + p.o_sin + (size_t)s_pos[b] * 64 + (i % 64)) : 0.f;
+  }
   {
     const int ngen = p.decode ? ldg_cg(&p.st->n_gen) : 0;
     for (int i = tid; i < BT * KC; i += MG_THREADS) {
@@ -455,38 +583,66 @@ __global__ void __launch_bounds__(MG_THREADS, 1) k_step(const MegaP p) {
     __syncthreads();
   }
 
-  const int S = max(1, min(p.nsplit_max, (2 * (int)gridDim.x + p.Hq * p.B - 1) / (p.Hq * p.B)));
+  int S = max(1, min(p.nsplit_max, (2 * (int)gridDim.x + p.Hq * p.B - 1) / (p.Hq * p.B)));
+  if (BT <= 2) S = min(S, MG_SMAX);
   float4 dw[MG_DOWN_PAIRS][2][3];
+  constexpr bool SMALL = BT <= 2;  // O-proj merges the attention splits itself; gate/up is fully prefetched
   for (int l = 0; l < p.L; ++l) {
     const float* Wl = W0 + (int64_t)l * p.layer_stride;
     float* kvl = p.kv + (size_t)l * p.kv_layer_floats;
     // A: QKV + RoPE + KV append   (l == 0: activations already staged from the input above)
     mg_gemv_phase<BT, MG_QKV>(p, c, Wl + p.o_wqkv, nqkv_tasks, nqkv_rows, p.x, Wl + p.o_ln1, kvl, w0, w1, l == 0);
-    {  // next weights: O-proj
+    grid_arrive(p.bar, epoch);
+    {  // next weights: O-proj (one task per warp)
       const int task = blockIdx.x * MG_WARPS + warp;
       if (task < p.d / 2) mg_load_w<MG_OPROJ>(p, Wl + p.o_wo, task, p.d, lane, w0, w1);
     }
-    grid_barrier(p.bar, epoch);
+    grid_wait(p.bar, epoch);
     MG_TRACE();
     // B: attention
-    mg_attn_phase<BT>(p, c, kvl, S);
-    grid_barrier(p.bar, epoch);
+    mg_attn_phase<BT, SMALL>(p, c, kvl, S);
+    grid_arrive(p.bar, epoch);
+    float rx0 = 0.f, rx1 = 0.f;
+    {  // residual values of this warp's O-proj task (x is stable since the previous down phase / the input)
+      constexpr int LPB_ = 32 / BT;
+      const int task = blockIdx.x * MG_WARPS + warp, b = lane / LPB_;
+      if (task < p.d / 2 && (lane % LPB_) == 0 && b < p.B) {
+        rx0 = ldg_cg(p.x + (size_t)b * p.d + 2 * task);
+        rx1 = ldg_cg(p.x + (size_t)b * p.d + 2 * task + 1);
+      }
+    }
+    grid_wait(p.bar, epoch);
     MG_TRACE();
     // C: O-proj + residual
-    mg_gemv_phase<BT, MG_OPROJ>(p, c, Wl + p.o_wo, p.d / 2, p.d, p.attn, nullptr, nullptr, w0, w1, false);
-    {
+    if (blockIdx.x * MG_WARPS < p.d / 2) {  // only the CTAs that own O-proj rows stage the attention output
+      if (SMALL) mg_attn_merge<BT>(p, c, S, gws);  // xs <- merged splits; the gate/up landing zone is free here
+      mg_gemv_phase<BT, MG_OPROJ>(p, c, Wl + p.o_wo, p.d / 2, p.d, p.attn, nullptr, nullptr, w0, w1, SMALL, rx0, rx1);
+    }
+    grid_arrive(p.bar, epoch);
+    if (SMALL) {
+      mg_gateup_load<BT>(p, Wl + p.o_wgu, lane, warp, gws);
+    } else {
       const int task = blockIdx.x * MG_WARPS + warp;
       if (task < p.I) mg_load_w<MG_GATEUP>(p, Wl + p.o_wgu, task, 2 * p.I, lane, w0, w1);
     }
-    grid_barrier(p.bar, epoch);
+    grid_wait(p.bar, epoch);
     MG_TRACE();
     // D: gate/up + SiLU*mul
-    mg_gemv_phase<BT, MG_GATEUP>(p, c, Wl + p.o_wgu, p.I, 2 * p.I, p.x, Wl + p.o_ln2, nullptr, w0, w1, false);
+    if (SMALL) mg_gateup_small<BT>(p, c, Wl + p.o_ln2, gws);
+    else mg_gemv_phase<BT, MG_GATEUP>(p, c, Wl + p.o_wgu, p.I, 2 * p.I, p.x, Wl + p.o_ln2, nullptr, w0, w1, false);
+    grid_arrive(p.bar, epoch);
     mg_down_load<BT>(p, Wl + p.o_wd, lane, warp, dw);
-    grid_barrier(p.bar, epoch);
+    float rxd = 0.f;
+    if (tid < MG_DOWN_PAIRS * 2 * BT) {  // residual of this thread's final-reduce element (stable since the O-proj phase)
+      const int b = tid % BT, r = (tid / BT) % 2, j = tid / (2 * BT);
+      const int pair = blockIdx.x + j * gridDim.x;
+      if (pair < p.d / 2 && b < p.B) rxd = ldg_cg(p.x + (size_t)b * p.d + 2 * pair + r);
+    }
+    grid_wait(p.bar, epoch);
     MG_TRACE();
     // E: down + residual
-    mg_down_phase<BT>(p, c, dw);
+    mg_down_phase<BT>(p, c, dw, rxd);
+    grid_arrive(p.bar, epoch);
     if (l + 1 < p.L) {
       const int task = blockIdx.x * MG_WARPS + warp;
       if (task < nqkv_tasks) mg_load_w<MG_QKV>(p, Wl + p.layer_stride + p.o_wqkv, task, nqkv_rows, lane, w0, w1);
@@ -495,7 +651,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) k_step(const MegaP p) {
       if (task < (p.rows_per_item * p.V + 1) / 2)
         mg_load_w<MG_HEADS>(p, p.W + p.o_head, task, p.rows_per_item * p.V, lane, w0, w1);
     }
-    grid_barrier(p.bar, epoch);
+    grid_wait(p.bar, epoch);
     MG_TRACE();
   }
   if (p.sample) {
