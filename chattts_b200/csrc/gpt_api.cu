@@ -63,7 +63,7 @@ struct ctb_gpt {
   bool use_tc, tc_ready;
   int tc_min_batch;
   bool mega_ok;      // one-kernel decode step (mega.cuh), built for B <= 8
-  int mega_max_batch; // batches that use it (default 1: measured faster only there; CTB_MEGA_MAX_BATCH overrides)
+  int mega_max_batch; // batches that use it (default 4: measured faster there; CTB_MEGA_MAX_BATCH overrides)
   unsigned* bar;     // its grid-barrier counter
   unsigned long long* trace;  // CTB_MEGA_TRACE=1: per-phase timestamps of the last step
   float *tc_wqkv, *tc_wgu, *tc_heads_code, *tc_heads_text;  // permuted / norm-folded weight copies
@@ -269,7 +269,7 @@ extern "C" int ctb_gpt_create(const ctb_gpt_config* c, const float* weights_dev,
   h->use_graph = getenv("CTB_NO_GRAPH") == nullptr;
   h->mega_ok = getenv("CTB_NO_MEGA") == nullptr && g_num_sms >= 128 && c->intermediate_size == 4 * KC &&
                (c->hidden_size / 2 + g_num_sms - 1) / g_num_sms <= MG_DOWN_PAIRS;
-  h->mega_max_batch = getenv("CTB_MEGA_MAX_BATCH") ? std::min(8, atoi(getenv("CTB_MEGA_MAX_BATCH"))) : 1;
+  h->mega_max_batch = getenv("CTB_MEGA_MAX_BATCH") ? std::min(8, atoi(getenv("CTB_MEGA_MAX_BATCH"))) : 4;
   // tensor-core decode GEMMs (tc_decode.cuh): CTB_GPT_TC=1 forces them for every batch, CTB_GPT_FMA=1 disables
   // them; by default they serve batches > 16 rows, where the fp32 FMA path turns compute-bound.
   h->tc_ready = getenv("CTB_GPT_FMA") == nullptr && c->max_batch <= 32 &&
@@ -493,8 +493,8 @@ static int launch_heads_tc(ctb_gpt* h, cudaStream_t s) {
 
 template <int BT>
 static int launch_step_mega_t(const MegaP& mp, cudaStream_t s) {
-  // [BT][3072] activations (down phase) + for BT <= 2 the gate/up weight landing zone
-  const size_t smem = (size_t)BT * 4 * KC * sizeof(float) + (BT <= 2 ? (size_t)MG_GW_FLOATS * sizeof(float) : 0);
+  // [BT][3072] activations (down phase) + for BT <= 4 the gate/up weight landing zone
+  const size_t smem = (size_t)BT * 4 * KC * sizeof(float) + (BT <= 4 ? (size_t)MG_GW_FLOATS * sizeof(float) : 0);
   static bool attr_done = false;
   if (!attr_done) {
     CTB_CUDA(cudaFuncSetAttribute(k_step<BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

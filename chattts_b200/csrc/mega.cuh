@@ -223,7 +223,7 @@ __device__ __forceinline__ void mg_gemv_phase(const MegaP& p, const MegaCtx<BT>&
   }
 }
 
-// gate/up for BT <= 2: all (<= 3) tasks of the warp were requested before the barrier (144 registers), so the phase
+// gate/up for BT <= 4: all (<= 3) tasks of the warp were requested before the barrier (144 registers), so the phase
 // exposes no DRAM round trip at all.
 constexpr int MG_GU_TASKS = 3;
 constexpr int MG_SMAX = 12;  // max attention splits per (row, head) when the O-proj phase merges them (BT <= 2)
@@ -410,7 +410,7 @@ __device__ __forceinline__ void mg_attn_phase(const MegaP& p, const MegaCtx<BT>&
   }
 }
 
-// BT <= 2: merge the flash-decoding partials of every (row, head) straight into the O-proj staging buffer xs[b][h*64+d]
+// BT <= 4: merge the flash-decoding partials of every (row, head) straight into the O-proj staging buffer xs[b][h*64+d]
 // (each CTA redundantly; 12 x S x 66 floats per row from L2) - no atomics / fences / last-CTA pass in the attention phase.
 template <int BT>
 __device__ __forceinline__ void mg_attn_merge(const MegaP& p, const MegaCtx<BT>& c, int S, float* scratch) {
@@ -527,7 +527,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) k_step(const MegaP p) {
   __shared__ int s_pos[BT], s_active[BT], s_page[BT];
   __shared__ float s_cos[BT * 64], s_sin[BT * 64];
   MegaCtx<BT> c{mg_smem, s_rinv, s_pos, s_active, s_cos, s_sin, s_page};
-  float* gws = mg_smem + BT * 4 * KC;  // BT <= 2 only: gate/up weight landing zone behind the activation buffer
+  float* gws = mg_smem + BT * 4 * KC;  // BT <= 4 only: gate/up weight landing zone behind the activation buffer
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   pdl_trigger();
   const float* W0 = p.W + p.layer0;
@@ -583,10 +583,11 @@ __global__ void __launch_bounds__(MG_THREADS, 1) k_step(const MegaP p) {
     __syncthreads();
   }
 
-  int S = max(1, min(p.nsplit_max, (2 * (int)gridDim.x + p.Hq * p.B - 1) / (p.Hq * p.B)));
-  if (BT <= 2) S = min(S, MG_SMAX);
+  // one round of attention units: (row, head, split) <= #CTAs; each unit walks its chunks with a running softmax
+  int S = max(1, min(p.nsplit_max, (int)gridDim.x / (p.Hq * p.B)));
+  if (BT <= 4) S = min(S, MG_SMAX);
   float4 dw[MG_DOWN_PAIRS][2][3];
-  constexpr bool SMALL = BT <= 2;  // O-proj merges the attention splits itself; gate/up is fully prefetched
+  constexpr bool SMALL = BT <= 4;  // O-proj merges the attention splits itself; gate/up is fully prefetched
   for (int l = 0; l < p.L; ++l) {
     const float* Wl = W0 + (int64_t)l * p.layer_stride;
     float* kvl = p.kv + (size_t)l * p.kv_layer_floats;
