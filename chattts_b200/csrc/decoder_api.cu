@@ -1,6 +1,5 @@
 // extern "C" entry points for hot path 2 (token -> waveform); see include/chattts_b200.h.
-#include <cudaTypedefs.h>
-
+#define CTB_DECODER_KERNELS_IMPL
 #include "tc_gemm.cuh"
 
 using namespace ctb;
@@ -145,12 +144,6 @@ extern "C" int ctb_decoder_create(const ctb_convstack_config* dc, const float* d
     if (h->dW) k_split_tf32<<<1024, 256>>>(h->dW, h->dW_hi, h->dW_lo, h->dl.total);
     if (h->vW) k_split_tf32<<<1024, 256>>>(h->vW, h->vW_hi, h->vW_lo, h->vl.total);
     CTB_CUDA(cudaDeviceSynchronize());
-    CTB_CUDA(cudaFuncSetAttribute(k_tc_gemm<GE_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-    CTB_CUDA(cudaFuncSetAttribute(k_tc_gemm<GE_BIAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-    CTB_CUDA(cudaFuncSetAttribute(k_tc_gemm<GE_GELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-    CTB_CUDA(cudaFuncSetAttribute(k_tc_gemm<GE_SCALE_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-    CTB_CUDA(cudaFuncSetAttribute(k_tc_gemm<GE_COEF>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-    CTB_CUDA(cudaFuncSetAttribute(k_tc_gemm<GE_SPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
   }
   *out = h;
   return CTB_OK;
@@ -165,30 +158,6 @@ __global__ void k_split_tf32(const float* __restrict__ w, float* __restrict__ hi
   }
 }
 
-static PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
-  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
-  }
-  return fn;
-}
-
-static int make_map(CUtensorMap* m, const float* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                    const cuuint32_t* box) {
-  auto enc = tensor_map_encoder();
-  if (!enc) return set_err(CTB_ERR_CUDA, "cuTensorMapEncodeTiled unavailable");
-  const cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<float*>(base), dims, strides_bytes, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return set_err(CTB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
-  return CTB_OK;
-}
-
 struct GemmCtx {  // which blob a weight pointer lives in, for the hi / lo lookup of the tensor-core path
   const float* W; const float* hi; const float* lo; bool tc;
 };
@@ -197,27 +166,9 @@ template <int EPI>
 static int gemm(cudaStream_t s, const GemmCtx& gc, const float* A, int lda, int M, int N, int K, int taps, int Cin,
                 int dil, int pad, int F, const float* W, const float* bias, const float* gamma, const float* res,
                 int ldres, float* C, int ldc) {
-  if (gc.tc && K % TC_BK == 0 && Cin % TC_BK == 0 && M % F == 0) {
-    const int B = M / F;
-    CUtensorMap ma, mh, ml;
-    const cuuint64_t adims[3] = {(cuuint64_t)lda, (cuuint64_t)F, (cuuint64_t)B};
-    const cuuint64_t astr[2] = {(cuuint64_t)lda * 4, (cuuint64_t)F * lda * 4};
-    const cuuint32_t abox[3] = {TC_BK, TC_BM, 1};
-    const cuuint64_t wdims[2] = {(cuuint64_t)K, (cuuint64_t)N};
-    const cuuint64_t wstr[1] = {(cuuint64_t)K * 4};
-    const cuuint32_t wbox[2] = {TC_BK, TC_BN};
-    int rc;
-    if ((rc = make_map(&ma, A, 3, adims, astr, abox))) return rc;
-    if ((rc = make_map(&mh, gc.hi + (W - gc.W), 2, wdims, wstr, wbox))) return rc;
-    if ((rc = make_map(&ml, gc.lo + (W - gc.W), 2, wdims, wstr, wbox))) return rc;
-    TcGemmP p{};
-    p.N = N; p.K = K; p.taps = taps; p.Cin = Cin; p.dil = dil; p.pad = pad; p.F = F; p.B = B;
-    p.bias = bias; p.gamma = gamma; p.res = res; p.ldres = ldres; p.C = C; p.ldc = ldc;
-    dim3 grid((N + TC_BN - 1) / TC_BN, B * ((F + TC_BM - 1) / TC_BM));
-    k_tc_gemm<EPI><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(ma, mh, ml, p);
-    CTB_LAUNCH_CHECK();
-    return CTB_OK;
-  }
+  if (gc.tc && K % TC_BK == 0 && Cin % TC_BK == 0 && M % F == 0)
+    return tc_gemm_launch<EPI>(s, A, lda, M / F, F, N, K, taps, Cin, dil, pad, gc.hi + (W - gc.W), gc.lo + (W - gc.W), bias,
+                               gamma, res, ldres, C, ldc);
   GemmP p{};
   p.A = A; p.lda = lda; p.M = M; p.N = N; p.K = K; p.taps = taps; p.Cin = Cin; p.dil = dil; p.pad = pad; p.F = F;
   p.W = W; p.bias = bias; p.gamma = gamma; p.res = res; p.ldres = ldres; p.C = C; p.ldc = ldc;

@@ -219,6 +219,7 @@ __global__ void __launch_bounds__(256) k_dwconv_ln(const DwLnP p) {
   }
 }
 
+#ifdef CTB_DECODER_KERNELS_IMPL  // non-template kernels: defined once, in decoder_api.cu
 // [B, Cin2, T] channels-first -> time-major [B, 2T, Cin2/2] with the frame-doubling of
 // dvae.py:281-287 (channel c < C/2 -> even frame, c + C/2 -> odd frame).  Tiled transpose.
 __global__ void k_cf_to_tm_doubled(const float* __restrict__ in, float* __restrict__ out, int B, int C2, int T) {
@@ -321,5 +322,7 @@ __global__ void k_overlap_add(const float* __restrict__ frames, const float* __r
   }
   wav[i] = s / env;
 }
+
+#endif  // CTB_DECODER_KERNELS_IMPL
 
 }  // namespace ctb

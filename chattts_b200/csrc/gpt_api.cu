@@ -9,6 +9,8 @@
 #include "gpt_kernels.cuh"
 #include "tc_decode.cuh"
 #include "mega.cuh"
+#include "prefill.cuh"
+#include "tc_gemm.cuh"
 
 namespace ctb {
 
@@ -62,6 +64,12 @@ struct ctb_gpt {
   // ---- tensor-core decode path (tc_decode.cuh)
   bool use_tc, tc_ready;
   int tc_min_batch;
+  // ---- batched prefill (prefill.cuh): lazily allocated
+  bool pf_enabled;
+  float *gw_hi, *gw_lo;            // tf32 hi / lo copies of the per-layer weight region of the blob
+  float *pf_resid, *pf_xn, *pf_qkv, *pf_q, *pf_attn, *pf_gu, *pf_h, *pf_ones, *pf_zeros;
+  int *pf_npre, *pf_nvalid;
+  size_t pf_rows;                  // capacity (B * T0) of the pf_* activation buffers
   bool mega_ok;      // one-kernel decode step (mega.cuh), built for B <= 8
   int mega_max_batch; // batches that use it (default 4: measured faster there; CTB_MEGA_MAX_BATCH overrides)
   unsigned* bar;     // its grid-barrier counter
@@ -267,6 +275,7 @@ extern "C" int ctb_gpt_create(const ctb_gpt_config* c, const float* weights_dev,
   for (size_t i = 0; i < bt_host.size(); ++i) bt_host[i] = (int)i;
   cudaMemcpy(h->block_table, bt_host.data(), bt_host.size() * sizeof(int), cudaMemcpyHostToDevice);
   h->use_graph = getenv("CTB_NO_GRAPH") == nullptr;
+  h->pf_enabled = getenv("CTB_NO_BATCHED_PREFILL") == nullptr;
   h->mega_ok = getenv("CTB_NO_MEGA") == nullptr && g_num_sms >= 128 && c->intermediate_size == 4 * KC &&
                (c->hidden_size / 2 + g_num_sms - 1) / g_num_sms <= MG_DOWN_PAIRS;
   h->mega_max_batch = getenv("CTB_MEGA_MAX_BATCH") ? std::min(8, atoi(getenv("CTB_MEGA_MAX_BATCH"))) : 4;
@@ -286,7 +295,8 @@ extern "C" int ctb_gpt_destroy(ctb_gpt* h) {
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   void* ptrs[] = {h->x, h->qbuf, h->attn, h->mlp, h->logits, h->kv, h->part, h->block_table, h->seq_len,
                   h->pos, h->counter, h->end_idx, h->idx, h->active, h->finish, h->st, h->tc_wqkv, h->tc_wgu,
-                  h->tc_heads_code, h->tc_heads_text, h->x_hi, h->x_lo, h->attn_hi, h->attn_lo, h->h_hi, h->h_lo, h->bar, h->trace};
+                  h->tc_heads_code, h->tc_heads_text, h->x_hi, h->x_lo, h->attn_hi, h->attn_lo, h->h_hi, h->h_lo, h->bar, h->trace, h->gw_hi, h->gw_lo, h->pf_resid, h->pf_xn, h->pf_qkv, h->pf_q,
+                  h->pf_attn, h->pf_gu, h->pf_h, h->pf_ones, h->pf_zeros, h->pf_npre, h->pf_nvalid};
   delete[] h->m_wqkv; delete[] h->m_wo; delete[] h->m_wgu; delete[] h->m_wd;
   for (void* p : ptrs) if (p) cudaFree(p);
   delete h;
@@ -613,6 +623,96 @@ extern "C" int ctb_gpt_profile_kernel(ctb_gpt* h, int32_t kind, void* stream) {
   return CTB_OK;
 }
 
+// ------------------------------------------------------------------ batched prefill
+static int prefill_reserve(ctb_gpt* h, size_t rows) {
+  const ctb_gpt_config& c = h->cfg;
+  const size_t d = c.hidden_size, I = c.intermediate_size, nqkv = (size_t)(c.num_heads + 2 * c.num_kv_heads) * c.head_dim;
+  int rc;
+  if (!h->gw_hi) {
+    const size_t n = (size_t)h->lay.layer_stride * c.num_layers;
+    if ((rc = dalloc(&h->gw_hi, n))) return rc;
+    if ((rc = dalloc(&h->gw_lo, n))) return rc;
+    k_split_tf32_t<0><<<2048, 256>>>(h->W + h->lay.layer0, h->gw_hi, h->gw_lo, (int64_t)n);
+    if ((rc = dalloc(&h->pf_ones, 2 * I))) return rc;
+    if ((rc = dalloc(&h->pf_zeros, 2 * I))) return rc;
+    std::vector<float> ones(2 * I, 1.0f);
+    CTB_CUDA(cudaMemcpy(h->pf_ones, ones.data(), ones.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CTB_CUDA(cudaDeviceSynchronize());
+  }
+  if (rows > h->pf_rows) {
+    float** bufs[] = {&h->pf_resid, &h->pf_xn, &h->pf_qkv, &h->pf_q, &h->pf_attn, &h->pf_gu, &h->pf_h};
+    for (float** b : bufs) if (*b) { cudaFree(*b); *b = nullptr; }
+    if (h->pf_npre) { cudaFree(h->pf_npre); h->pf_npre = nullptr; }
+    if (h->pf_nvalid) { cudaFree(h->pf_nvalid); h->pf_nvalid = nullptr; }
+    if ((rc = dalloc(&h->pf_resid, rows * d))) return rc;
+    if ((rc = dalloc(&h->pf_xn, rows * d))) return rc;
+    if ((rc = dalloc(&h->pf_qkv, rows * nqkv))) return rc;
+    if ((rc = dalloc(&h->pf_q, rows * d))) return rc;
+    if ((rc = dalloc(&h->pf_attn, rows * d))) return rc;
+    if ((rc = dalloc(&h->pf_gu, rows * 2 * I))) return rc;
+    if ((rc = dalloc(&h->pf_h, rows * I))) return rc;
+    if ((rc = dalloc(&h->pf_npre, rows))) return rc;
+    if ((rc = dalloc(&h->pf_nvalid, (size_t)h->cfg.max_batch))) return rc;
+    h->pf_rows = rows;
+  }
+  return CTB_OK;
+}
+
+static int prefill_batched(ctb_gpt* h, cudaStream_t s) {
+  const ctb_gpt_config& c = h->cfg;
+  const ctb_gpt_layout& L = h->lay;
+  const int B = h->B, T0 = h->T0, M = B * T0;
+  const int d = c.hidden_size, I = c.intermediate_size, nqkv = (c.num_heads + 2 * c.num_kv_heads) * c.head_dim;
+  int rc;
+  if ((rc = prefill_reserve(h, (size_t)M))) return rc;
+  CTB_CUDA(cudaMemcpyAsync(h->pf_resid, h->emb, (size_t)M * d * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  k_prefill_positions<<<B, 32, 0, s>>>(h->mask, h->pf_npre, h->pf_nvalid, T0);
+  CTB_LAUNCH_CHECK();
+  PrefillP pp{};
+  pp.B = B; pp.T0 = T0; pp.Hq = c.num_heads; pp.Hkv = c.num_kv_heads; pp.hd = c.head_dim; pp.d = d; pp.mask = h->mask;
+  pp.npre = h->pf_npre; pp.nvalid = h->pf_nvalid; pp.qkv = h->pf_qkv; pp.q = h->pf_q; pp.block_table = h->block_table;
+  pp.pages_per_row = h->pages_per_row; pp.rope_cos = h->W + L.rope_cos; pp.rope_sin = h->W + L.rope_sin;
+  pp.permute_qk = h->use_tc ? 1 : 0; pp.attn = h->pf_attn; pp.scaling = 1.0f / sqrtf((float)c.head_dim);
+  const int rms_blocks = (M + 7) / 8;
+  for (int l = 0; l < c.num_layers; ++l) {
+    const int64_t lo = (int64_t)l * L.layer_stride;
+    const float* Wl = h->W + L.layer0 + lo;
+    const float *Whi = h->gw_hi + lo, *Wlo = h->gw_lo + lo;
+    pp.kv = h->kv + (size_t)l * h->kv_layer_floats;
+    k_rms_rows<<<rms_blocks, 256, 0, s>>>(h->pf_resid, Wl + L.ln1, h->pf_xn, M, d, c.rms_eps);
+    CTB_LAUNCH_CHECK();
+    if ((rc = tc_gemm_launch<GE_NONE>(s, h->pf_xn, d, B, T0, nqkv, d, 1, d, 1, 0, Whi + L.wqkv, Wlo + L.wqkv, nullptr,
+                                      nullptr, nullptr, 0, h->pf_qkv, nqkv))) return rc;
+    k_prefill_rope_kv<<<dim3(T0, B), 256, 0, s>>>(pp);
+    CTB_LAUNCH_CHECK();
+    k_prefill_attn<<<dim3(c.num_heads, B), 128, (size_t)T0 * sizeof(float), s>>>(pp);
+    CTB_LAUNCH_CHECK();
+    if ((rc = tc_gemm_launch<GE_SCALE_RES>(s, h->pf_attn, d, B, T0, d, d, 1, d, 1, 0, Whi + L.wo, Wlo + L.wo, h->pf_zeros,
+                                           h->pf_ones, h->pf_resid, d, h->pf_resid, d))) return rc;
+    k_rms_rows<<<rms_blocks, 256, 0, s>>>(h->pf_resid, Wl + L.ln2, h->pf_xn, M, d, c.rms_eps);
+    CTB_LAUNCH_CHECK();
+    if ((rc = tc_gemm_launch<GE_NONE>(s, h->pf_xn, d, B, T0, 2 * I, d, 1, d, 1, 0, Whi + L.wgate_up, Wlo + L.wgate_up,
+                                      nullptr, nullptr, nullptr, 0, h->pf_gu, 2 * I))) return rc;
+    k_silu_mul<<<(unsigned)(((size_t)M * I + 255) / 256), 256, 0, s>>>(h->pf_gu, h->pf_h, M, I);
+    CTB_LAUNCH_CHECK();
+    if ((rc = tc_gemm_launch<GE_SCALE_RES>(s, h->pf_h, I, B, T0, d, I, 1, I, 1, 0, Whi + L.wdown, Wlo + L.wdown,
+                                           h->pf_zeros, h->pf_ones, h->pf_resid, d, h->pf_resid, d))) return rc;
+  }
+  k_prefill_finish<<<B, 256, 0, s>>>(h->pf_resid, h->x, h->use_tc ? h->x_hi : nullptr, h->use_tc ? h->x_lo : nullptr,
+                                     h->pf_nvalid, h->seq_len, h->pos, h->active, T0, d);
+  CTB_LAUNCH_CHECK();
+  // first token: heads -> sampler -> finalize (the i == 0 iteration of gpt.py:394)
+  const StepCtx x = make_ctx(h, 0);
+  if ((rc = h->use_tc ? launch_heads_tc(h, s) : launch_heads(h, x, s))) return rc;
+  if ((rc = launch_sampler(h, x, s))) return rc;
+  FinalP fp{};
+  fp.st = h->st; fp.B = B; fp.rows_per_item = h->infer_text ? 1 : c.num_vq; fp.num_vq = c.num_vq; fp.max_new = h->max_new;
+  fp.eos = h->sampler.eos_token; fp.idx = h->idx; fp.ids_out = h->ids_out; fp.finish = h->finish; fp.end_idx = h->end_idx;
+  CTB_CUDA(launch_pdl(k_finalize, dim3(1), dim3(256), 0, s, fp));
+  CTB_LAUNCH_CHECK();
+  return CTB_OK;
+}
+
 extern "C" int ctb_gpt_begin(ctb_gpt* h, int32_t B, int32_t T0, const float* emb_dev, const uint8_t* mask_dev,
                              const ctb_sampler_config* sampler, const float* q_noise_dev, int32_t max_new_token,
                              int32_t infer_text, int32_t* ids_out_dev, float* hiddens_out_dev, void* stream) {
@@ -642,8 +742,15 @@ extern "C" int ctb_gpt_begin(ctb_gpt* h, int32_t B, int32_t T0, const float* emb
   int rc;
   // prefill: the prompt is walked column by column through the decode kernels (left padding
   // keeps every row's last prompt token in the last column, like the reference's batches)
-  for (int col = 0; col < T0; ++col)
-    if ((rc = enqueue_step(h, col, col == T0 - 1, s))) return rc;
+  if (h->pf_enabled && T0 >= 8 && T0 <= 1024) {
+    // whole prompt as token-parallel tcgen05 GEMMs (prefill.cuh)
+    if ((rc = prefill_batched(h, s))) return rc;
+  } else {
+    // short prompts: walk the columns through the decode kernels (left padding keeps every row's last prompt
+    // token in the last column, like the reference's batches)
+    for (int col = 0; col < T0; ++col)
+      if ((rc = enqueue_step(h, col, col == T0 - 1, s))) return rc;
+  }
   h->started = 1;
   return CTB_OK;
 }

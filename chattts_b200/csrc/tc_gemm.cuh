@@ -14,6 +14,7 @@
 //     [A | A_lo | W_hi | W_lo], 128-byte swizzle (TMA and UMMA descriptors agree).
 #pragma once
 #include <cuda.h>
+#include <cudaTypedefs.h>
 
 #include "decoder_kernels.cuh"
 #include "tc_common.cuh"
@@ -182,6 +183,66 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   if (warp == 5) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TC_BN));
+  }
+}
+
+// ---------------------------------------------------------------- host launcher (shared by both C APIs)
+inline int tc_make_map(CUtensorMap* m, const float* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                       const cuuint32_t* box) {
+  static PFN_cuTensorMapEncodeTiled_v12000 enc = nullptr;
+  if (!enc) {
+    void* fp = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return set_err(CTB_ERR_CUDA, "cuTensorMapEncodeTiled unavailable");
+    enc = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fp);
+  }
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<float*>(base), dims, strides_bytes, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_err(CTB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return CTB_OK;
+}
+
+// C[B*F rows, N] = epi(A (x) W^T): A time-major [B][F][lda], W given as tf32 hi / lo copies [N][K]
+template <int EPI>
+inline int tc_gemm_launch(cudaStream_t s, const float* A, int lda, int B, int F, int N, int K, int taps, int Cin, int dil,
+                          int pad, const float* W_hi, const float* W_lo, const float* bias, const float* gamma,
+                          const float* res, int ldres, float* C, int ldc) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    CTB_CUDA(cudaFuncSetAttribute(k_tc_gemm<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    attr_done = true;
+  }
+  CUtensorMap ma, mh, ml;
+  const cuuint64_t adims[3] = {(cuuint64_t)lda, (cuuint64_t)F, (cuuint64_t)B};
+  const cuuint64_t astr[2] = {(cuuint64_t)lda * 4, (cuuint64_t)F * lda * 4};
+  const cuuint32_t abox[3] = {TC_BK, TC_BM, 1};
+  const cuuint64_t wdims[2] = {(cuuint64_t)K, (cuuint64_t)N};
+  const cuuint64_t wstr[1] = {(cuuint64_t)K * 4};
+  const cuuint32_t wbox[2] = {TC_BK, TC_BN};
+  int rc;
+  if ((rc = tc_make_map(&ma, A, 3, adims, astr, abox))) return rc;
+  if ((rc = tc_make_map(&mh, W_hi, 2, wdims, wstr, wbox))) return rc;
+  if ((rc = tc_make_map(&ml, W_lo, 2, wdims, wstr, wbox))) return rc;
+  TcGemmP p{};
+  p.N = N; p.K = K; p.taps = taps; p.Cin = Cin; p.dil = dil; p.pad = pad; p.F = F; p.B = B;
+  p.bias = bias; p.gamma = gamma; p.res = res; p.ldres = ldres; p.C = C; p.ldc = ldc;
+  dim3 grid((N + TC_BN - 1) / TC_BN, B * ((F + TC_BM - 1) / TC_BM));
+  k_tc_gemm<EPI><<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(ma, mh, ml, p);
+  CTB_LAUNCH_CHECK();
+  return CTB_OK;
+}
+
+// tf32 hi / lo split of a weight buffer (device side, once at load)
+template <int DUMMY = 0>
+__global__ void k_split_tf32_t(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float x = w[i], h = to_tf32(x);
+    hi[i] = h;
+    lo[i] = to_tf32(x - h);
   }
 }
 

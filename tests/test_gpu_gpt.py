@@ -82,7 +82,8 @@ def test_greedy_processor_and_larger_weights():
     out = _run(gpt, embed, [9, 14], 4, 1, 20, extra=(ArgmaxOnly(exclude_eos=True),))[-1]
     for b in range(2):
         assert torch.equal(out.ids[b].cpu(), ref.ids[b])
-        assert (out.hiddens[b].cpu() - ref.hiddens[b]).abs().max() < 2e-4
+        # |hidden| reaches ~4 with these weights and reorder noise compounds over 20 layers: 1e-4 relative
+        assert (out.hiddens[b].cpu() - ref.hiddens[b]).abs().max() < 5e-4
 
 
 @pytest.mark.parametrize("V,rpi,rows", [(626, 4, 32), (626, 4, 8), (21178, 1, 6)])
@@ -215,3 +216,36 @@ def test_unseeded_generation_uses_device_philox_and_is_valid():
         assert all(t.shape == (24, 4) and int(t.min()) >= 0 and int(t.max()) < 626 for t in o.ids)
         outs.append(torch.stack(o.ids))
     assert not torch.equal(outs[0], outs[1])  # fresh Philox stream per call (no parity target)
+
+
+def test_batched_prefill_long_ragged_prompts():
+    """prompts of 40..128 tokens, left padded, go through the token-parallel tcgen05 prefill
+    (prefill.cuh); ids must equal the CPU oracle's and the column-by-column prefill's."""
+    import os
+
+    from chattts_b200.config import Config
+    from chattts_b200.embed import Embed
+    from chattts_b200.gpt import GPT
+    from chattts_b200.synth import synth_embed_state, synth_gpt_state
+
+    gs, es = synth_gpt_state(0), synth_embed_state(1)
+    lengths = [40, 128, 77]
+    orc = GPTOracle(gs, es)
+    ids, mask, tmask = synth_prompt_batch(lengths, seed=23)
+    ref = orc.generate(orc.embed_prompt(ids, tmask), ids, torch.tensor([0.3] * 4), 625, attention_mask=mask,
+                       max_new_token=10, min_new_token=10, sampler=SamplerParams(), return_hidden=True, manual_seed=5)
+    outs = {}
+    for tag, env in (("batched", {}), ("columns", {"CTB_NO_BATCHED_PREFILL": "1"})):
+        os.environ.update(env)
+        try:
+            embed = Embed(768, 626, 21178, 4).load_state_dict(es).to("cuda")
+            gpt = GPT(Config().gpt, embed, device="cuda", device_gpt="cuda", max_batch=3, max_context=160)
+            gpt.load_state(gs)
+            outs[tag] = _run(gpt, embed, lengths, 23, 5, 10)[-1]
+        finally:
+            for k in env:
+                os.environ.pop(k, None)
+    for b in range(3):
+        assert torch.equal(outs["batched"].ids[b].cpu(), ref.ids[b]), b
+        assert torch.equal(outs["columns"].ids[b].cpu(), ref.ids[b]), b
+        assert (outs["batched"].hiddens[b].cpu() - ref.hiddens[b]).abs().max() < 1e-4
