@@ -71,7 +71,7 @@ struct ctb_gpt {
   int *pf_npre, *pf_nvalid;
   size_t pf_rows;                  // capacity (B * T0) of the pf_* activation buffers
   bool mega_ok;      // one-kernel decode step (mega.cuh), built for B <= 8
-  int mega_max_batch; // batches that use it (default 4: measured faster there; CTB_MEGA_MAX_BATCH overrides)
+  int mega_max_batch; // batches that use it (default 4: measured faster up to there; CTB_MEGA_MAX_BATCH overrides)
   unsigned* bar;     // its grid-barrier counter
   unsigned long long* trace;  // CTB_MEGA_TRACE=1: per-phase timestamps of the last step
   float *tc_wqkv, *tc_wgu, *tc_heads_code, *tc_heads_text;  // permuted / norm-folded weight copies
@@ -503,8 +503,9 @@ static int launch_heads_tc(ctb_gpt* h, cudaStream_t s) {
 
 template <int BT>
 static int launch_step_mega_t(const MegaP& mp, cudaStream_t s) {
-  // [BT][3072] activations (down phase) + for BT <= 4 the gate/up weight landing zone
-  const size_t smem = (size_t)BT * 4 * KC * sizeof(float) + (BT <= 4 ? (size_t)MG_GW_FLOATS * sizeof(float) : 0);
+  // [BT][768] activations + the 144 KiB landing zone (gate/up weights; reused as merge scratch and for the down
+  // phase's [BT][3072] activations)
+  const size_t smem = (size_t)BT * KC * sizeof(float) + (size_t)MG_GW_FLOATS * sizeof(float);
   static bool attr_done = false;
   if (!attr_done) {
     CTB_CUDA(cudaFuncSetAttribute(k_step<BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -226,6 +226,7 @@ __device__ __forceinline__ void mg_gemv_phase(const MegaP& p, const MegaCtx<BT>&
 // gate/up for BT <= 4: all (<= 3) tasks of the warp were requested before the barrier (144 registers), so the phase
 // exposes no DRAM round trip at all.
 constexpr int MG_GU_TASKS = 3;
+__host__ __device__ constexpr int mg_chunk(int BT) { return BT >= 4 ? 128 : 64; }  // keys per attention chunk
 constexpr int MG_SMAX = 12;  // max attention splits per (row, head) when the O-proj phase merges them (BT <= 2)
 // Shared-memory landing zone for the warp's gate/up weights: [warp][task][row][192 float4] (18 KiB per warp).
 // cp.async needs no registers, so all 36 x 16 B requests per lane are in flight while the CTA waits at the barrier.
@@ -289,7 +290,7 @@ __device__ __forceinline__ void mg_gateup_small(const MegaP& p, const MegaCtx<BT
 // attention phase: units (b, h, s) strided over the grid; unit s walks key chunks s, s + S, ... with a running softmax
 template <int BT, bool DEFER>
 __device__ __forceinline__ void mg_attn_phase(const MegaP& p, const MegaCtx<BT>& c, const float* kvl, int S) {
-  constexpr int HD = 64, NW = MG_WARPS, CH = ATT_CHUNK, PER_WARP = CH / NW, ITER = PER_WARP / 4;
+  constexpr int HD = 64, NW = MG_WARPS, CH = mg_chunk(BT), PER_WARP = CH / NW, ITER = PER_WARP / 4;
   static_assert(ITER >= 1, "attention chunk too small for the warp count");
   __shared__ float s_m[NW], s_l[NW];
   __shared__ __align__(16) float s_o[NW][HD];
@@ -432,7 +433,7 @@ __device__ __forceinline__ void mg_attn_merge(const MegaP& p, const MegaCtx<BT>&
     float v = 0.f;
     if (b < p.B && c.active[b]) {
       const int n = c.pos[b] + 1;
-      const int nsplit = min((n + ATT_CHUNK - 1) / ATT_CHUNK, S);
+      const int nsplit = min((n + mg_chunk(BT) - 1) / mg_chunk(BT), S);
       const float* pb = scratch + (size_t)b * per_row + (size_t)h * S * PW;
       float GM = -INFINITY;
       for (int s = 0; s < nsplit; ++s) GM = fmaxf(GM, pb[s * PW + HD]);
@@ -469,15 +470,16 @@ __device__ __forceinline__ void mg_down_load(const MegaP& p, const float* Wd, in
 }
 
 template <int BT>
-__device__ __forceinline__ void mg_down_phase(const MegaP& p, const MegaCtx<BT>& c, float4 (&dw)[MG_DOWN_PAIRS][2][3], float rx) {
+__device__ __forceinline__ void mg_down_phase(const MegaP& p, const MegaCtx<BT>& c, float4 (&dw)[MG_DOWN_PAIRS][2][3], float rx,
+                                              float* xs) {
   __shared__ float red[MG_DOWN_PAIRS][MG_WARPS][2][BT];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nb = p.B, npairs = p.d / 2, I4 = p.I / 4;
   // stage mlp [BT][I]
   for (int i = tid; i < BT * I4; i += MG_THREADS) {
     const int b = i / I4, k4 = i % I4;
-    if (b < nb) cp_async16(&c.xs[i * 4], p.mlp + (size_t)b * p.I + k4 * 4);
-    else reinterpret_cast<float4*>(c.xs)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (b < nb) cp_async16(&xs[i * 4], p.mlp + (size_t)b * p.I + k4 * 4);
+    else reinterpret_cast<float4*>(xs)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   cp_async_wait_all();
   __syncthreads();
@@ -494,7 +496,7 @@ __device__ __forceinline__ void mg_down_phase(const MegaP& p, const MegaCtx<BT>&
     for (int i = 0; i < 3; ++i) {
 #pragma unroll
       for (int b = 0; b < BT; ++b) {
-        const float4 xv = reinterpret_cast<const float4*>(c.xs)[b * I4 + kq + i * 32 + lane];
+        const float4 xv = reinterpret_cast<const float4*>(xs)[b * I4 + kq + i * 32 + lane];
         acc0[b] = fmaf(dw[j][0][i].x, xv.x, acc0[b]); acc0[b] = fmaf(dw[j][0][i].y, xv.y, acc0[b]);
         acc0[b] = fmaf(dw[j][0][i].z, xv.z, acc0[b]); acc0[b] = fmaf(dw[j][0][i].w, xv.w, acc0[b]);
         acc1[b] = fmaf(dw[j][1][i].x, xv.x, acc1[b]); acc1[b] = fmaf(dw[j][1][i].y, xv.y, acc1[b]);
@@ -527,7 +529,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) k_step(const MegaP p) {
   __shared__ int s_pos[BT], s_active[BT], s_page[BT];
   __shared__ float s_cos[BT * 64], s_sin[BT * 64];
   MegaCtx<BT> c{mg_smem, s_rinv, s_pos, s_active, s_cos, s_sin, s_page};
-  float* gws = mg_smem + BT * 4 * KC;  // BT <= 4 only: gate/up weight landing zone behind the activation buffer
+  float* gws = mg_smem + BT * KC;  // gate/up weight landing zone (also: attention-merge scratch, down-phase activations)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   pdl_trigger();
   const float* W0 = p.W + p.layer0;
@@ -585,9 +587,9 @@ __global__ void __launch_bounds__(MG_THREADS, 1) k_step(const MegaP p) {
 
   // one round of attention units: (row, head, split) <= #CTAs; each unit walks its chunks with a running softmax
   int S = max(1, min(p.nsplit_max, (int)gridDim.x / (p.Hq * p.B)));
-  if (BT <= 4) S = min(S, MG_SMAX);
+  S = min(S, MG_SMAX);
   float4 dw[MG_DOWN_PAIRS][2][3];
-  constexpr bool SMALL = BT <= 4;  // O-proj merges the attention splits itself; gate/up is fully prefetched
+  constexpr bool SMALL = true;  // O-proj merges the attention splits itself; gate/up streams through the landing zone
   for (int l = 0; l < p.L; ++l) {
     const float* Wl = W0 + (int64_t)l * p.layer_stride;
     float* kvl = p.kv + (size_t)l * p.kv_layer_floats;
@@ -642,7 +644,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) k_step(const MegaP p) {
     grid_wait(p.bar, epoch);
     MG_TRACE();
     // E: down + residual
-    mg_down_phase<BT>(p, c, dw, rxd);
+    mg_down_phase<BT>(p, c, dw, rxd, gws);  // [BT][3072] activations staged in the (now free) landing zone
     grid_arrive(p.bar, epoch);
     if (l + 1 < p.L) {
       const int task = blockIdx.x * MG_WARPS + warp;
