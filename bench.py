@@ -214,8 +214,10 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         achieved = kbytes / (us * 1e-6) / 1e9
         roofline = {"bound": "hbm", "kernel": "k_step<1> (one launch = the whole decode step: 20 layers + heads, 101 phases)",
                     "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                    "traffic": None, "peak_source": peak_src, "bytes_per_launch": int(kbytes),
-                    "us_per_launch": round(us, 2)}
+                    "traffic": 771580416, "peak_source": peak_src, "bytes_per_launch": int(kbytes),
+                    "us_per_launch": round(us, 2),
+                    "traffic_note": "dram__bytes_read+write of one k_step<1> launch at context 64 from ncu --set full "
+                                    "(profiles/r01_k_step_b1_full_raw.csv); algorithmic bytes at that context: 770.8 MB"}
     else:
         for kind, name in ((3, "gateup"), (4, "down"), (0, "qkv"), (2, "oproj"), (1, "k_attn"), (5, "heads"), (6, "k_sample")):
             kern[name] = time_kind(kind, 20, 20 if kind < 5 else 1)
@@ -311,6 +313,25 @@ def bench_decoder(dev, B: int = 64, T: int = 469):
             "rtf": round((ms / 1e3) / (wav.numel() / 24000.0), 7), "tflops_fp32_equiv": round(flops / (ms / 1e3) / 1e12, 1)}
 
 
+def best_cpu_threads(run4, candidates=(16, 32, 64, 128)):
+    """Pick the torch thread count that makes the oracle port fastest on this host (the reference arm must use the
+    host as well as it can; more threads are not always faster for a batch-1 GEMV chain)."""
+    cores = os.cpu_count() or 1
+    best, best_t = None, None
+    for n in candidates:
+        if n > cores:
+            break
+        torch.set_num_threads(n)
+        run4()
+        t = run4()
+        if best_t is None or t < best_t:
+            best, best_t = n, t
+    if best is None:
+        best = cores
+    torch.set_num_threads(best)
+    return best
+
+
 def cpu_baseline_sample(B: int, budget_s: float = 15.0):
     """The oracle port (torch fp32 CPU, same ops as the reference's HF path) on this host's cores,
     on a bounded sample of the same workload."""
@@ -319,8 +340,6 @@ def cpu_baseline_sample(B: int, budget_s: float = 15.0):
     from oracle.gpt_oracle import GPTOracle, SamplerParams
 
     cores = os.cpu_count() or 1
-    threads = min(cores, 32)
-    torch.set_num_threads(threads)
     orc = GPTOracle(synth_gpt_state(0), synth_embed_state(1))
     ids, mask, tmask = synth_prompt_batch([PROMPT_LEN] * B, seed=1)
     sp = SamplerParams(greedy=True, greedy_exclude_eos=True)
@@ -331,7 +350,7 @@ def cpu_baseline_sample(B: int, budget_s: float = 15.0):
                      max_new_token=n, min_new_token=n, sampler=sp, manual_seed=1234)
         return time.perf_counter() - t
 
-    run(2)
+    threads = best_cpu_threads(lambda: run(4))
     t4 = run(4)
     n = int(max(8, min(256, budget_s / max(t4 / 4, 1e-3))))
     t = run(n)
@@ -350,16 +369,21 @@ def run_reference(args, rank: int):
     from oracle.gpt_oracle import GPTOracle, SamplerParams
 
     cores = os.cpu_count() or 1
-    threads = min(cores, 32)
-    torch.set_num_threads(threads)
     B, n = args.batch, args.ref_tokens
     orc = GPTOracle(synth_gpt_state(0), synth_embed_state(1))
     ids, mask, tmask = synth_prompt_batch([PROMPT_LEN] * B, seed=1)
     sp = SamplerParams(greedy=True, greedy_exclude_eos=True)
 
-    def step():
+    def gen(k):
+        t = time.perf_counter()
         orc.generate(orc.embed_prompt(ids, tmask), ids, torch.tensor([0.3] * 4), 625, attention_mask=mask,
-                     max_new_token=n, min_new_token=n, sampler=sp, manual_seed=1234)
+                     max_new_token=k, min_new_token=k, sampler=sp, manual_seed=1234)
+        return time.perf_counter() - t
+
+    threads = best_cpu_threads(lambda: gen(4))
+
+    def step():
+        gen(n)
 
     for _ in range(args.warmup):
         step()
