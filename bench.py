@@ -262,7 +262,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             torch.cuda.empty_cache()
         sweep["decoder_c4"] = bench_decoder(dev)
 
-    cpu = cpu_baseline_sample(B)
+    # the CPU baseline is timed on rank 0 at N = 1 only (it would otherwise compete with the other ranks' host threads)
+    cpu = cpu_baseline_sample(B) if world == 1 else None
     audio_s = B * tokens * 512 / 24000.0
     line = {
         "metric": "speech-tokens/sec (GPT decode loop, 4-codebook tokens; RTF = wall / audio seconds @ 24 kHz)",

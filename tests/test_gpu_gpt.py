@@ -249,3 +249,28 @@ def test_batched_prefill_long_ragged_prompts():
         assert torch.equal(outs["batched"].ids[b].cpu(), ref.ids[b]), b
         assert torch.equal(outs["columns"].ids[b].cpu(), ref.ids[b]), b
         assert (outs["batched"].hiddens[b].cpu() - ref.hiddens[b]).abs().max() < 1e-4
+
+
+def test_full_batch_rows_are_independent_of_batch_and_back_end():
+    """BASELINE configs[2] scale: 32 mixed-length prompts decoded greedily in one batch (tcgen05 GEMM back end +
+    batched prefill) must give, row by row, the ids of the same prompt decoded alone (one-kernel back end):
+    rows never interact and every back end computes the same function."""
+    from gpu_util import build_gpt
+
+    big, embed, _, _ = build_gpt(max_batch=32, max_context=256)
+    solo, _, _, _ = build_gpt(max_batch=1, max_context=256)
+    g = torch.Generator().manual_seed(31)
+    lengths = torch.randint(8, 129, (32,), generator=g).tolist()
+    steps = 48
+    batch = _run(big, embed, lengths, 41, 1, steps, extra=(ArgmaxOnly(exclude_eos=True),))[-1]
+    ids, mask, tmask = synth_prompt_batch(lengths, seed=41)
+    warp, proc = gen_logits(num_code=625, top_P=0.7, top_K=20, repetition_penalty=1.05)
+    for b in (0, 7, 13, 31):
+        n = lengths[b]
+        row_ids = ids[b: b + 1, ids.shape[1] - n:]
+        row_mask = torch.ones(1, n, dtype=torch.bool)
+        out = list(solo.generate(embed(row_ids, row_mask), row_ids, temperature=torch.tensor([0.3] * 4), eos_token=625,
+                                 attention_mask=row_mask, max_new_token=steps, min_new_token=steps,
+                                 logits_processors=(*proc, *warp, ArgmaxOnly(exclude_eos=True)), return_hidden=False,
+                                 show_tqdm=False, manual_seed=1))[-1]
+        assert torch.equal(out.ids[0].cpu(), batch.ids[b].cpu()), b
