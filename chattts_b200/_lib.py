@@ -55,7 +55,7 @@ class VocosConfig(C.Structure):
 #: every symbol include/chattts_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = (
     "ctb_abi_version", "ctb_last_error", "ctb_launch_count", "ctb_gpt_layout_query", "ctb_gpt_create",
-    "ctb_gpt_destroy", "ctb_gpt_begin", "ctb_gpt_decode", "ctb_gpt_status_query", "ctb_gpt_profile_kernel", "ctb_gpt_debug_trace", "ctb_sample",
+    "ctb_gpt_destroy", "ctb_gpt_begin", "ctb_gpt_decode", "ctb_gpt_status_query", "ctb_gpt_profile_kernel", "ctb_gpt_debug_trace", "ctb_gpt_embed_prompt", "ctb_sample",
     "ctb_dvae_blob_floats", "ctb_vocos_blob_floats", "ctb_decoder_create", "ctb_decoder_destroy",
     "ctb_dvae_decode", "ctb_vocos_decode",
 )
@@ -93,6 +93,7 @@ def load(build_if_missing: bool = True):
         lib.ctb_gpt_status_query.argtypes = [vp, C.POINTER(GptStatus), vp, vp, vp]
         lib.ctb_gpt_profile_kernel.argtypes = [vp, i32, vp]
         lib.ctb_gpt_debug_trace.argtypes = [vp, vp, i32]
+        lib.ctb_gpt_embed_prompt.argtypes = [vp, vp, vp, i32, i32, vp, vp]
         lib.ctb_sample.argtypes = [vp, i32, i32, i32, C.POINTER(SamplerConfig), vp, vp, i32, i32, i32, vp, vp]
         lib.ctb_dvae_blob_floats.argtypes = [C.POINTER(ConvStackConfig)]
         lib.ctb_dvae_blob_floats.restype = i64

@@ -787,6 +787,43 @@ extern "C" int ctb_gpt_decode(ctb_gpt* h, int32_t n_steps, void* stream) {
   return CTB_OK;
 }
 
+namespace ctb {
+// Embed.forward (embed.py:51-79): one CTA per prompt position
+__global__ void k_embed_prompt(const int64_t* __restrict__ ids, const uint8_t* __restrict__ text_mask,
+                               const float* __restrict__ emb_text, const float* __restrict__ emb_code, int num_vq,
+                               int num_audio, int num_text, int d, float* __restrict__ out) {
+  const size_t pos = blockIdx.x;
+  const int64_t* id = ids + pos * num_vq;
+  float* o = out + pos * d;
+  if (text_mask[pos]) {
+    const int64_t t = min(max(id[0], (int64_t)0), (int64_t)num_text - 1);
+    const float* e = emb_text + (size_t)t * d;
+    for (int k = threadIdx.x; k < d; k += blockDim.x) o[k] = e[k];
+  } else {
+    for (int k = threadIdx.x; k < d; k += blockDim.x) {
+      float s = 0.f;
+      for (int q = 0; q < num_vq; ++q) {
+        const int64_t c = min(max(id[q], (int64_t)0), (int64_t)num_audio - 1);
+        s += emb_code[((size_t)q * num_audio + c) * d + k];
+      }
+      o[k] = s;
+    }
+  }
+}
+}  // namespace ctb
+
+extern "C" int ctb_gpt_embed_prompt(ctb_gpt* h, const int64_t* ids_dev, const uint8_t* text_mask_dev, int32_t B, int32_t T,
+                                    float* out_dev, void* stream) {
+  if (!h || !ids_dev || !text_mask_dev || !out_dev) return set_err(CTB_ERR_ARG, "null argument");
+  if (B < 1 || T < 1) return set_err(CTB_ERR_ARG, "bad shape");
+  const ctb_gpt_config& c = h->cfg;
+  k_embed_prompt<<<(unsigned)((size_t)B * T), 256, 0, (cudaStream_t)stream>>>(
+      ids_dev, text_mask_dev, h->W + h->lay.emb_text, h->W + h->lay.emb_code, c.num_vq, c.num_audio_tokens,
+      c.num_text_tokens, c.hidden_size, out_dev);
+  CTB_LAUNCH_CHECK();
+  return CTB_OK;
+}
+
 extern "C" int ctb_gpt_debug_trace(ctb_gpt* h, unsigned long long* host_out, int n) {
   if (!h || !h->trace) return set_err(CTB_ERR_STATE, "trace disabled (set CTB_MEGA_TRACE=1 before ctb_gpt_create)");
   CTB_CUDA(cudaMemcpy(host_out, h->trace, sizeof(unsigned long long) * (size_t)std::min(n, 256), cudaMemcpyDeviceToHost));

@@ -306,25 +306,3 @@ def decode_to_wavs(result_list: Sequence[torch.Tensor], use_decoder: bool, decod
             batch[i, :, : r.size(0)] = r.to(dev).permute(1, 0)
         wav = eng.tokens_to_wav(batch, 2)
     return wav.cpu().numpy()
-
-
-def smoke_decoder():
-    """Tiny path-2 run checked against the CPU oracle (used by __graft_entry__.smoke)."""
-    from oracle.dvae_oracle import dvae_decode as o_dvae, vocos_decode as o_vocos
-    from .synth import synth_dvae_state, synth_vocos_state
-
-    cfg = Config()
-    vs, ds = synth_vocos_state(5), synth_dvae_state(2, cfg.decoder, cfg.decoder.idim)
-    voc = Vocos(cfg.vocos, "cuda:0", max_batch=2, max_tokens=16)
-    voc.state = vs
-    dec = DVAE(cfg.decoder, dim=cfg.decoder.idim, device="cuda:0", vocos=voc, max_batch=2, max_tokens=16)
-    dec.load_state_dict(ds)
-    x = torch.randn(2, 768, 9)
-    mel = dec(x)
-    ref_mel = o_dvae(x, ds)
-    assert (mel.cpu() - ref_mel).abs().max() < 1e-4, "mel differs from oracle"
-    wav = dec.engine.vocos_decode(mel)
-    ref = o_vocos(ref_mel, vs)
-    rms = float((wav.cpu() - ref).pow(2).mean().sqrt())
-    assert rms < 1e-4, f"waveform RMS error {rms}"
-    print(f"smoke decoder ok: wav rms err {rms:.2e}")

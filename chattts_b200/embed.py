@@ -19,6 +19,7 @@ class Embed:
         self.num_vq = num_vq
         self.state: Dict[str, torch.Tensor] = {}
         self.device = torch.device("cpu")
+        self._gpt = None  # set by GPT.load_state: the tables then live in the packed blob of that handle
 
     # embed.py:37-41
     def load_pretrained(self, filename: str, device: torch.device):
@@ -55,6 +56,8 @@ class Embed:
     def __call__(self, input_ids: torch.Tensor, text_mask: torch.Tensor) -> torch.Tensor:
         """Prompt embedding mix (embed.py:51-79): text rows use ``emb_text(ids[...,0])``, the
         others the sum of the four code embeddings."""
+        if self._gpt is not None and self._gpt._handle:
+            return self._gpt.embed_prompt(input_ids, text_mask)
         dev = self.device
         ids = input_ids.to(dev)
         tm = text_mask.to(dev).bool()

@@ -121,6 +121,22 @@ class GPT:
             self._handle = C.c_void_p()
         with torch.cuda.device(self.device_gpt):
             _lib.check(lib.ctb_gpt_create(C.byref(cc), C.c_void_p(self._weights.data_ptr()), C.byref(self._handle)))
+        self.embed._gpt = self  # Embed.forward now runs as ctb_gpt_embed_prompt on this handle's tables
+
+    @torch.inference_mode()
+    def embed_prompt(self, input_ids: torch.Tensor, text_mask: torch.Tensor) -> torch.Tensor:
+        """Embed.forward (embed.py:51-79) on the device: [B, T, num_vq] ids + text mask -> [B, T, d] fp32."""
+        lib = _lib.load()
+        dev = self.device_gpt
+        ids = input_ids.to(dev, torch.int64).contiguous()
+        tm = text_mask.to(dev).to(torch.uint8).contiguous()
+        B, T = int(ids.shape[0]), int(ids.shape[1])
+        out = torch.empty(B, T, self.config.hidden_size, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.ctb_gpt_embed_prompt(self._handle, C.c_void_p(ids.data_ptr()), C.c_void_p(tm.data_ptr()), B, T,
+                                                C.c_void_p(out.data_ptr()),
+                                                C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        return out
 
     def query_layout(self):
         """(ctb_gpt_config, ctb_gpt_layout) for this model shape - the C side owns the blob layout."""

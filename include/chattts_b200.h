@@ -142,6 +142,12 @@ int ctb_gpt_profile_kernel(ctb_gpt* h, int32_t kind, void* stream);
  * a %globaltimer stamp (ns) of CTA 0 after every grid barrier of the most recent step; copies up to n of them. */
 int ctb_gpt_debug_trace(ctb_gpt* h, unsigned long long* host_out, int n);
 
+/* Prompt embedding mix: replaces Embed.forward (ChatTTS/model/embed.py:51-79).
+ *   ids_dev [B, T, num_vq] int64 (tokenizer output), text_mask_dev [B, T] uint8, tables inside the packed blob of `h`;
+ *   out_dev [B, T, d] fp32: text positions get emb_text[ids[...,0]], the others sum_q emb_code[q][ids[...,q]]. */
+int ctb_gpt_embed_prompt(ctb_gpt* h, const int64_t* ids_dev, const uint8_t* text_mask_dev, int32_t B, int32_t T,
+                         float* out_dev, void* stream);
+
 /* Stand-alone sampling tail over caller-provided logits (minimum slice of SURVEY.md 7.2;
  * same kernel the decode loop uses).
  *   logits_dev [rows, V] fp32 (not modified); gen_ids_dev [rows/rpi, gen_stride, rpi] int32 with

@@ -274,3 +274,17 @@ def test_full_batch_rows_are_independent_of_batch_and_back_end():
                                  logits_processors=(*proc, *warp, ArgmaxOnly(exclude_eos=True)), return_hidden=False,
                                  show_tqdm=False, manual_seed=1))[-1]
         assert torch.equal(out.ids[0].cpu(), batch.ids[b].cpu()), b
+
+
+def test_embed_prompt_kernel_matches_reference_embed_semantics():
+    """Embed.forward (embed.py:51-79) through ctb_gpt_embed_prompt vs the oracle restatement, with mixed text/code
+    positions (audio-prompt splice, tokenizer.py:115-124)."""
+    from gpu_util import build_gpt
+
+    gpt, embed, gs, es = build_gpt()
+    orc = GPTOracle(gs, es)
+    ids, mask, tmask = synth_prompt_batch([6, 3, 9], seed=5)
+    tmask[0, -2:] = False
+    ids[0, -2:] = torch.randint(0, 626, (2, 4))
+    got = embed(ids, tmask)
+    assert got.is_cuda and torch.equal(got.cpu(), orc.embed_prompt(ids, tmask))
