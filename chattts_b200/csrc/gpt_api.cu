@@ -317,7 +317,9 @@ static int launch_gemv_t(const GemvP& p, int ntiles, cudaStream_t s) {
   unsigned cluster = 1;
   if (EPI == EPI_DOWN) {
     cluster = DOWN_SPLIT;
-    const int groups = std::max(1, std::min(g_num_sms / DOWN_SPLIT, (p.ntasks + GEMV_WARPS - 1) / GEMV_WARPS));
+    // clusters of 4 can only occupy ~132 of the 148 SMs at once (GPC granularity): one wave of 33 clusters, not 37
+    const int max_groups = (g_num_sms * 132 / 148) / DOWN_SPLIT;
+    const int groups = std::max(1, std::min(max_groups, (p.ntasks + GEMV_WARPS - 1) / GEMV_WARPS));
     if ((p.ntasks + groups * GEMV_WARPS - 1) / (groups * GEMV_WARPS) > DOWN_MAX_TASKS)
       return set_err(CTB_ERR_STATE, "DOWN kernel: too few SMs (%d) for %d tasks", g_num_sms, p.ntasks);
     ctas = groups * DOWN_SPLIT;
@@ -337,6 +339,28 @@ static int launch_gemv(int bt, const GemvP& p, int ntiles, cudaStream_t s) {
     case 8: return launch_gemv_t<8, EPI>(p, ntiles, s);
     case 16: return launch_gemv_t<16, EPI>(p, ntiles, s);
     default: return launch_gemv_t<32, EPI>(p, ntiles, s);
+  }
+}
+
+template <int BT>
+static int launch_down_small_t(const GemvP& p, cudaStream_t s) {
+  const size_t smem = (size_t)BT * p.K * sizeof(float);
+  static bool attr_done = false;
+  if (!attr_done) {
+    CTB_CUDA(cudaFuncSetAttribute(k_down_small<BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  CTB_CUDA(launch_pdl(k_down_small<BT>, dim3(g_num_sms), dim3(GEMV_WARPS * 32), smem, s, p));
+  CTB_LAUNCH_CHECK();
+  return CTB_OK;
+}
+static int launch_down_small(int bt, const GemvP& p, cudaStream_t s) {
+  switch (bt) {
+    case 1: return launch_down_small_t<1>(p, s);
+    case 2: return launch_down_small_t<2>(p, s);
+    case 4: return launch_down_small_t<4>(p, s);
+    case 8: return launch_down_small_t<8>(p, s);
+    default: return launch_down_small_t<16>(p, s);
   }
 }
 
@@ -414,6 +438,9 @@ static int launch_layer_kernel(ctb_gpt* h, const StepCtx& x, int l, int kind, cu
       return launch_gemv<EPI_GATEUP>(x.bt, p, x.ntiles, s);
     case 4:
       p.W = Wl + L.wdown; p.K = I; p.nrows = d; p.ntasks = d / 2; p.xin = h->mlp; p.normw = nullptr;
+      if (x.bt <= 16 && x.ntiles == 1 && I == 4 * KC && (d / 2 + g_num_sms - 1) / g_num_sms <= DS_PAIRS &&
+          getenv("CTB_DOWN_CLUSTER") == nullptr)
+        return launch_down_small(x.bt, p, s);
       return launch_gemv<EPI_DOWN>(x.bt, p, x.ntiles, s);
   }
   return set_err(CTB_ERR_ARG, "bad kernel kind %d", kind);

@@ -280,6 +280,78 @@ __global__ void __launch_bounds__(GEMV_WARPS * 32) k_gemv(const GemvP p) {
   }
 }
 
+// Down projection (K = I = 4 * KC) for batch tiles <= 16: no cluster.  Every CTA owns up to DS_PAIRS row pairs, its 8 warps
+// split K (I/8 each), ALL of the warp's weights are requested before griddepcontrol.wait (one DRAM round trip), the
+// batch tile's [BT][I] activations are staged once with cp.async, partial sums meet in shared memory in a fixed order.
+constexpr int DS_PAIRS = 3;  // ceil((d/2) / grid) for grid >= 128 CTAs
+template <int BT>
+__global__ void __launch_bounds__(GEMV_WARPS * 32) k_down_small(const GemvP p) {
+  pdl_trigger();
+  extern __shared__ __align__(16) float xs[];  // [BT][I]
+  __shared__ float red[DS_PAIRS][GEMV_WARPS][2][BT];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int I = p.K, d = p.nrows, npairs = d / 2, I4 = I / 4, ks4 = I4 / GEMV_WARPS;  // float4 per K slice (96)
+  float4 dw[DS_PAIRS][2][3];
+#pragma unroll
+  for (int j = 0; j < DS_PAIRS; ++j) {
+    const int pair = blockIdx.x + j * gridDim.x;
+    if (pair < npairs) {
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const float4* wp = reinterpret_cast<const float4*>(p.W + (size_t)(2 * pair + r) * I) + warp * ks4 + lane;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) dw[j][r][i] = ldg_stream(wp + i * 32);
+      }
+    }
+  }
+  pdl_wait();
+  if (p.check_finished && ldg_cg(&p.st->all_finished)) return;
+  const int nb = p.B;
+  for (int i = tid; i < BT * I4; i += GEMV_WARPS * 32) {
+    const int b = i / I4, k4 = i % I4;
+    if (b < nb) cp_async16(&xs[i * 4], p.xin + (size_t)b * I + k4 * 4);
+    else reinterpret_cast<float4*>(xs)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  // residual values of the final-reduce elements (one per thread), requested together with the activations
+  float rx = 0.f;
+  const bool fin = tid < DS_PAIRS * 2 * BT;
+  const int fb = tid % BT, fr = (tid / BT) % 2, fj = tid / (2 * BT);
+  const int fpair = blockIdx.x + fj * gridDim.x;
+  if (fin && fpair < npairs && fb < nb) rx = ldg_cg(p.xres + (size_t)fb * d + 2 * fpair + fr);
+  cp_async_wait_all();
+  __syncthreads();
+  constexpr int LPB = 32 / BT;
+#pragma unroll
+  for (int j = 0; j < DS_PAIRS; ++j) {
+    const int pair = blockIdx.x + j * gridDim.x;
+    if (pair >= npairs) break;
+    float acc0[BT], acc1[BT];
+#pragma unroll
+    for (int b = 0; b < BT; ++b) { acc0[b] = 0.f; acc1[b] = 0.f; }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+      for (int b = 0; b < BT; ++b) {
+        const float4 xv = reinterpret_cast<const float4*>(xs)[b * I4 + warp * ks4 + i * 32 + lane];
+        acc0[b] = fmaf(dw[j][0][i].x, xv.x, acc0[b]); acc0[b] = fmaf(dw[j][0][i].y, xv.y, acc0[b]);
+        acc0[b] = fmaf(dw[j][0][i].z, xv.z, acc0[b]); acc0[b] = fmaf(dw[j][0][i].w, xv.w, acc0[b]);
+        acc1[b] = fmaf(dw[j][1][i].x, xv.x, acc1[b]); acc1[b] = fmaf(dw[j][1][i].y, xv.y, acc1[b]);
+        acc1[b] = fmaf(dw[j][1][i].z, xv.z, acc1[b]); acc1[b] = fmaf(dw[j][1][i].w, xv.w, acc1[b]);
+      }
+    }
+    warp_reduce_scatter<BT>(acc0);
+    warp_reduce_scatter<BT>(acc1);
+    if ((lane % LPB) == 0) { red[j][warp][0][lane / LPB] = acc0[0]; red[j][warp][1][lane / LPB] = acc1[0]; }
+  }
+  __syncthreads();
+  if (fin && fpair < npairs && fb < nb) {
+    float v = red[fj][0][fr][fb];
+#pragma unroll
+    for (int w = 1; w < GEMV_WARPS; ++w) v = __fadd_rn(v, red[fj][w][fr][fb]);  // K slices in the order 0..7
+    p.xres[(size_t)fb * d + 2 * fpair + fr] = __fadd_rn(rx, v);
+  }
+}
+
 // ------------------------------------------------------------------ step input
 struct InputP {
   LoopState* st;
