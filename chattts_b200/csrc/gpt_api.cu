@@ -343,6 +343,28 @@ static int launch_gemv(int bt, const GemvP& p, int ntiles, cudaStream_t s) {
 }
 
 template <int BT>
+static int launch_gateup_small_t(const GemvP& p, cudaStream_t s) {
+  const size_t smem = ((size_t)BT * KC + GU_ZONE_FLOATS) * sizeof(float);
+  static bool attr_done = false;
+  if (!attr_done) {
+    CTB_CUDA(cudaFuncSetAttribute(k_gateup_small<BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  CTB_CUDA(launch_pdl(k_gateup_small<BT>, dim3(g_num_sms), dim3(GEMV_WARPS * 32), smem, s, p));
+  CTB_LAUNCH_CHECK();
+  return CTB_OK;
+}
+static int launch_gateup_small(int bt, const GemvP& p, cudaStream_t s) {
+  switch (bt) {
+    case 1: return launch_gateup_small_t<1>(p, s);
+    case 2: return launch_gateup_small_t<2>(p, s);
+    case 4: return launch_gateup_small_t<4>(p, s);
+    case 8: return launch_gateup_small_t<8>(p, s);
+    default: return launch_gateup_small_t<16>(p, s);
+  }
+}
+
+template <int BT>
 static int launch_down_small_t(const GemvP& p, cudaStream_t s) {
   const size_t smem = (size_t)BT * p.K * sizeof(float);
   static bool attr_done = false;
@@ -435,6 +457,9 @@ static int launch_layer_kernel(ctb_gpt* h, const StepCtx& x, int l, int kind, cu
     case 3:
       p.W = Wl + L.wgate_up; p.K = d; p.nrows = 2 * I; p.ntasks = I; p.xin = h->x; p.normw = Wl + L.ln2;
       p.out = h->mlp;
+      if (x.bt <= 8 && x.ntiles == 1 && (I + g_num_sms * GEMV_WARPS - 1) / (g_num_sms * GEMV_WARPS) <= GU_TASKS &&
+          getenv("CTB_GATEUP_GENERIC") == nullptr)
+        return launch_gateup_small(x.bt, p, s);
       return launch_gemv<EPI_GATEUP>(x.bt, p, x.ntiles, s);
     case 4:
       p.W = Wl + L.wdown; p.K = I; p.nrows = d; p.ntasks = d / 2; p.xin = h->mlp; p.normw = nullptr;

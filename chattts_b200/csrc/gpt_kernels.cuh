@@ -352,6 +352,89 @@ __global__ void __launch_bounds__(GEMV_WARPS * 32) k_down_small(const GemvP p) {
   }
 }
 
+// Gate/up projection for batch tiles <= 16: the (<= GU_TASKS) 2-row tasks of every warp land in a shared-memory zone through
+// cp.async issued BEFORE griddepcontrol.wait (no registers, every request in flight at once), so after the wait the kernel
+// only stages x, normalises and multiplies.  One CTA per SM.
+constexpr int GU_TASKS = 3;  // ceil(I / (grid * 8)) for grid >= 128 CTAs
+constexpr int GU_ZONE_FLOATS = GEMV_WARPS * GU_TASKS * 2 * KC;
+template <int BT>
+__global__ void __launch_bounds__(GEMV_WARPS * 32) k_gateup_small(const GemvP p) {
+  pdl_trigger();
+  extern __shared__ __align__(16) float gsm[];  // [BT][KC] activations | weight zone
+  __shared__ float rinv[BT];
+  float* xs = gsm;
+  float* zone = gsm + BT * KC;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tstride = gridDim.x * GEMV_WARPS;
+#pragma unroll
+  for (int j = 0; j < GU_TASKS; ++j) {
+    const int task = blockIdx.x * GEMV_WARPS + warp + j * tstride;
+    if (task < p.I) {
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const float* src = p.W + (size_t)(r ? p.I + task : task) * KC;
+        float* dst = zone + ((size_t)(warp * GU_TASKS + j) * 2 + r) * KC;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) cp_async16(dst + (i * 32 + lane) * 4, src + (i * 32 + lane) * 4);
+      }
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  pdl_wait();
+  if (p.check_finished && ldg_cg(&p.st->all_finished)) { cp_async_wait_all(); return; }
+  const int nb = p.B;
+  for (int i = tid; i < BT * (KC / 4); i += GEMV_WARPS * 32) {
+    const int b = i / (KC / 4), k4 = i % (KC / 4);
+    if (b < nb) cp_async16(&xs[i * 4], p.xin + (size_t)b * KC + k4 * 4);
+    else reinterpret_cast<float4*>(xs)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  cp_async_wait_all();  // activations and the weight zone
+  __syncthreads();
+  for (int b = warp; b < BT; b += GEMV_WARPS) {
+    float ss = 0.f;
+#pragma unroll
+    for (int k = lane; k < KC; k += 32) { const float v = xs[b * KC + k]; ss = fmaf(v, v, ss); }
+    ss = warp_sum(ss);
+    if (lane == 0) rinv[b] = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(__fdiv_rn(ss, (float)KC), p.eps)));
+  }
+  __syncthreads();
+  for (int i = tid; i < BT * KC; i += GEMV_WARPS * 32) {
+    const int b = i / KC, k = i % KC;
+    xs[i] = __fmul_rn(__ldg(p.normw + k), __fmul_rn(xs[i], rinv[b]));
+  }
+  __syncthreads();
+  constexpr int LPB = 32 / BT;
+#pragma unroll
+  for (int j = 0; j < GU_TASKS; ++j) {
+    const int task = blockIdx.x * GEMV_WARPS + warp + j * tstride;
+    if (task >= p.I) break;
+    const float4* g0 = reinterpret_cast<const float4*>(zone + ((size_t)(warp * GU_TASKS + j) * 2) * KC);
+    const float4* g1 = g0 + KC / 4;
+    float acc0[BT], acc1[BT];
+#pragma unroll
+    for (int b = 0; b < BT; ++b) { acc0[b] = 0.f; acc1[b] = 0.f; }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const float4 a = g0[i * 32 + lane], bq = g1[i * 32 + lane];
+#pragma unroll
+      for (int b = 0; b < BT; ++b) {
+        const float4 xv = reinterpret_cast<const float4*>(xs)[b * (KC / 4) + i * 32 + lane];
+        acc0[b] = fmaf(a.x, xv.x, acc0[b]); acc0[b] = fmaf(a.y, xv.y, acc0[b]);
+        acc0[b] = fmaf(a.z, xv.z, acc0[b]); acc0[b] = fmaf(a.w, xv.w, acc0[b]);
+        acc1[b] = fmaf(bq.x, xv.x, acc1[b]); acc1[b] = fmaf(bq.y, xv.y, acc1[b]);
+        acc1[b] = fmaf(bq.z, xv.z, acc1[b]); acc1[b] = fmaf(bq.w, xv.w, acc1[b]);
+      }
+    }
+    warp_reduce_scatter<BT>(acc0);
+    warp_reduce_scatter<BT>(acc1);
+    if ((lane % LPB) == 0 && (lane / LPB) < nb) {
+      const float v0 = acc0[0], v1 = acc1[0];
+      const float sg = __fdiv_rn(v0, __fadd_rn(1.0f, expf(-v0)));
+      p.out[(size_t)(lane / LPB) * p.I + task] = __fmul_rn(sg, v1);
+    }
+  }
+}
+
 // ------------------------------------------------------------------ step input
 struct InputP {
   LoopState* st;
