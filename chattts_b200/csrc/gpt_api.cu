@@ -242,7 +242,7 @@ extern "C" int ctb_gpt_create(const ctb_gpt_config* c, const float* weights_dev,
   ctb_gpt_layout_query(c, &h->lay);
   h->W = weights_dev;
   h->pages_per_row = (c->max_context + kPageTokens - 1) / kPageTokens;
-  h->nsplit_max = (c->max_context + ATT_CHUNK - 1) / ATT_CHUNK;
+  h->nsplit_max = (c->max_context + ATT_SPLIT_UNIT - 1) / ATT_SPLIT_UNIT;
   const int bt = bt_for(c->max_batch);
   h->bpad_max = ((c->max_batch + bt - 1) / bt) * bt;
   const size_t Bp = h->bpad_max, d = c->hidden_size;

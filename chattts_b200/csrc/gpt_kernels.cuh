@@ -21,8 +21,9 @@ struct LoopState {
 
 constexpr int KC = 768;        // K chunk staged in shared memory (= hidden size of the model)
 constexpr int GEMV_WARPS = 8;  // warps per CTA, one 2-row task per warp
-constexpr int ATT_CHUNK = 64;  // tokens per attention CTA (flash-decoding split)
-constexpr int ATT_THREADS = 128;
+constexpr int ATT_CHUNK = 128;      // keys per k_attn chunk: 8 warps x 16 keys, all K/V rows of a chunk in flight at once
+constexpr int ATT_THREADS = 256;
+constexpr int ATT_SPLIT_UNIT = 64;  // granularity the split/partial buffers are sized with (k_step uses 64-key chunks)
 
 enum Epi { EPI_QKV = 0, EPI_OPROJ = 1, EPI_GATEUP = 2, EPI_DOWN = 3, EPI_HEADS = 4 };
 
