@@ -66,6 +66,38 @@ def exp_noise(rows: int, cols: int, seed: int) -> torch.Tensor:
     return torch.empty(rows, cols, dtype=torch.float32).exponential_(1, generator=g)
 
 
+def decision_margins(logits: torch.Tensor, generated: torch.Tensor, temperature: torch.Tensor, sp: "SamplerParams",
+                     q: torch.Tensor, eos: int, ban_eos: bool):
+    """How close one sampling pass is to flipping under fp32 reorder noise (the 'margin monitor' of SURVEY.md 7):
+    returns (relative gap between the two largest p/q values, distance of the top-p cumulative sum from its
+    threshold at the cut), both minimised over the rows.  Used by the tests to show the committed fixtures sit far
+    (>= 1e-4) from any tie, so ~1e-6 differences in logits cannot change an id."""
+    x = apply_temperature(logits, temperature)
+    if sp.repetition_penalty is not None and sp.repetition_penalty != 1:
+        x = repetition_penalty(generated, x, sp.repetition_penalty, sp.penalty_max_ids, sp.penalty_window)
+    p_margin = float("inf")
+    if sp.top_p is not None:
+        srt, _ = torch.sort(x, descending=False)
+        cum = srt.softmax(dim=-1).cumsum(dim=-1)
+        thr = 1 - sp.top_p
+        p_margin = float((cum[..., :-sp.min_keep] - thr).abs().min())
+        x = top_p_filter(x, sp.top_p, sp.min_keep)
+    if sp.top_k is not None:
+        x = top_k_filter(x, sp.top_k, sp.min_keep)
+    if sp.greedy:
+        if sp.greedy_exclude_eos:
+            x = x.clone()
+            x[:, eos] = -float("inf")
+        x = x.masked_fill(x < x.max(dim=-1, keepdim=True)[0], -float("inf"))
+    if ban_eos:
+        x = x.clone()
+        x[:, eos] = -float("inf")
+    r = F.softmax(x, dim=-1) / q
+    top2 = torch.topk(r, 2, dim=-1)[0]
+    a_margin = float(((top2[:, 0] - top2[:, 1]) / top2[:, 0]).min())
+    return a_margin, p_margin
+
+
 def sample_from_scores(scores: torch.Tensor, q: torch.Tensor) -> torch.Tensor:
     """``torch.multinomial(scores, 1, generator)`` == ``argmax(scores / q)`` (ATen fast path)."""
     return torch.argmax(scores / q, dim=-1)
@@ -246,7 +278,7 @@ class GPTOracle:
         assert manual_seed is not None, "oracle covers the seeded path (unseeded has no parity target)"
         q = exp_noise(rows, V, manual_seed)
         past, hiddens = None, []
-        tr = {"logits": [], "sampled": []} if trace else None
+        tr = {"logits": [], "sampled": [], "argmax_margin": [], "top_p_margin": []} if trace else None
         progress = T0
         steps = 0
         for i in range(max_new_token):
@@ -269,6 +301,9 @@ class GPTOracle:
             idx = idx.view(B, -1)
             if trace:
                 tr["sampled"].append(idx.clone())
+                am, pm = decision_margins(logits, gen_rows, temperature, sampler, q, eos_token, i < min_new_token)
+                tr["argmax_margin"].append(am)
+                tr["top_p_margin"].append(pm)
             finish |= (idx == eos_token).any(1)
             app = idx if forced_ids is None else forced_ids[:, i]
             ids_buf[:, progress] = app if not infer_text else app[:, :1].expand(-1, nvq)
