@@ -387,7 +387,7 @@ static int launch_down_small(int bt, const GemvP& p, cudaStream_t s) {
 }
 
 static int launch_sample(const SampleP& sp, cudaStream_t s) {
-  const size_t smem = (size_t)sp.V * sizeof(float) + 1024 * sizeof(uint32_t);
+  const size_t smem = (size_t)sp.V * sizeof(float) + 2 * 1024 * sizeof(uint32_t);
   static size_t attr_max = 0;
   if (smem > attr_max) {
     CTB_CUDA(cudaFuncSetAttribute(k_sample, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -903,7 +903,7 @@ extern "C" int ctb_sample(const float* logits_dev, int32_t rows, int32_t V, int3
                           int32_t gen_stride, int32_t n_gen, int32_t step, int32_t* out_idx_dev, void* stream) {
   if (!logits_dev || !sampler || !out_idx_dev) return set_err(CTB_ERR_ARG, "null argument");
   if (rows < 1 || V < 1 || rows_per_item < 1 || rows % rows_per_item) return set_err(CTB_ERR_ARG, "bad shape");
-  if ((size_t)V * 4 + 4096 > 200 * 1024) return set_err(CTB_ERR_ARG, "V=%d too large for the sampler", V);
+  if ((size_t)V * 4 + 8192 > 200 * 1024) return set_err(CTB_ERR_ARG, "V=%d too large for the sampler", V);
   if (sampler->penalty_on && n_gen > 0 && !gen_ids_dev) return set_err(CTB_ERR_ARG, "gen_ids required");
   SampleP sp{};
   sp.st = nullptr; sp.check_finished = 0; sp.logits = logits_dev; sp.rows = rows; sp.V = V;

@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) k_sample(const SampleP p) {
   if (p.check_finished && ldg_cg(&p.st->all_finished)) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* s_x = reinterpret_cast<float*>(smem_raw);                 // [V] processed logits
-  uint32_t* s_key = reinterpret_cast<uint32_t*>(s_x + p.V);        // [1024] sort path only
+  uint32_t* s_key = reinterpret_cast<uint32_t*>(s_x + p.V);        // [2][1024] sort path only
   __shared__ double s_redd[SAMPLE_THREADS / 32];
   __shared__ int s_redi[SAMPLE_THREADS / 32];
   __shared__ float s_redf[SAMPLE_THREADS / 32];
@@ -122,20 +122,30 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) k_sample(const SampleP p) {
     const float denf = (float)den;
     const float pthr = (float)(1.0 - (double)c.top_p);  // `cum <= (1 - top_p)` evaluated in fp32
     if (V <= 1024) {
-      // ---------- sort path: bitonic sort of 1024 keys (pads = 0 sort first)
-      s_key[tid] = tid < V ? float_key(s_x[tid]) : 0u;
-      __syncthreads();
+      // ---------- sort path: bitonic sort of 1024 keys (pads = 0 sort first).  One key per thread in a register;
+      // compare-exchange distances < 32 are warp shuffles, the 15 longer ones go through two alternating
+      // shared-memory buffers (one barrier each instead of 55 barriers for an all-shared-memory network).
+      uint32_t key = tid < V ? float_key(s_x[tid]) : 0u;
+      int sb = 0;
       for (int k = 2; k <= 1024; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
-          const int ixj = tid ^ j;
-          if (ixj > tid) {
-            const uint32_t a = s_key[tid], b = s_key[ixj];
-            const bool up = (tid & k) == 0;
-            if ((a > b) == up) { s_key[tid] = b; s_key[ixj] = a; }
+          uint32_t other;
+          if (j >= 32) {
+            uint32_t* buf = s_key + sb * 1024;
+            buf[tid] = key;
+            __syncthreads();
+            other = buf[tid ^ j];
+            sb ^= 1;
+          } else {
+            other = __shfl_xor_sync(0xffffffffu, key, j);
           }
-          __syncthreads();
+          const bool up = (tid & k) == 0, lower = (tid & j) == 0;
+          key = (lower == up) ? min(key, other) : max(key, other);
         }
       }
+      __syncthreads();
+      s_key[tid] = key;
+      __syncthreads();
       uint32_t t_p = 0;
       if (use_p) {
         // inclusive scan (double, like ATen's CPU cumsum) of softmax(sorted) ascending
