@@ -76,10 +76,16 @@ def load(build_if_missing: bool = True):
         if _lib is not None:
             return _lib
         path = lib_path()
+        if build_if_missing:
+            # build() is a no-op when the digest of csrc/ + include/ matches the stamp beside the library, so an
+            # edited kernel is never silently ignored; a box without nvcc keeps using the library that travelled
+            try:
+                _build.build()
+            except Exception:
+                if not os.path.exists(path):
+                    raise
         if not os.path.exists(path):
-            if not build_if_missing:
-                raise CtbError(f"{path} missing: run `python -m chattts_b200.build`")
-            _build.build()
+            raise CtbError(f"{path} missing: run `python -m chattts_b200.build`")
         lib = C.CDLL(path)
         vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
         lib.ctb_abi_version.restype = C.c_int

@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(LIB_DIR, "libchattts_b200.so")
 SOURCES = ["gpt_api.cu", "sampler.cu", "decoder_api.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-    "-Xcompiler", "-fPIC", "--use_fast_math=false" if False else "-Xcompiler", "-O2",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-O2",
 ]
 
 
@@ -51,7 +51,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     for s in srcs:
         o = os.path.join(LIB_DIR, os.path.basename(s) + ".o")
         objs.append(o)
-        cmd = [_nvcc(), *NVCC_FLAGS, "-dc" if False else "-c", s, "-o", o]
+        cmd = [_nvcc(), *NVCC_FLAGS, "-c", s, "-o", o]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))

@@ -7,6 +7,8 @@
 #include <string.h>
 
 #include <atomic>
+#include <map>
+#include <mutex>
 #include <utility>
 
 #include "../../include/chattts_b200.h"
@@ -34,6 +36,20 @@ int set_err(int code, const char* fmt, ...);
       return ::ctb::set_err(CTB_ERR_CUDA, "%s:%d launch -> %s", __FILE__, __LINE__,         \
                             cudaGetErrorString(_e));                                        \
   } while (0)
+
+// cudaFuncSetAttribute is per device: remember (function, device) -> largest dynamic shared memory size set so far.
+inline int ensure_smem_attr(const void* fn, int bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, int> done;
+  int dev = 0;
+  CTB_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(mu);
+  int& cur = done[std::make_pair(fn, dev)];
+  if (cur >= bytes && cur > 0) return CTB_OK;
+  CTB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  cur = bytes;
+  return CTB_OK;
+}
 
 constexpr int kPageTokens = 16;
 

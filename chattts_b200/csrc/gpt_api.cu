@@ -1,6 +1,8 @@
 // extern "C" entry points for hot path 1 (see include/chattts_b200.h).
 #include <stdarg.h>
 
+#include <map>
+#include <mutex>
 #include <vector>
 
 #include <cudaTypedefs.h>
@@ -9,6 +11,7 @@
 #include "gpt_kernels.cuh"
 #include "tc_decode.cuh"
 #include "mega.cuh"
+#include "flow.cuh"
 #include "prefill.cuh"
 #include "tc_gemm.cuh"
 
@@ -26,6 +29,7 @@ int set_err(int code, const char* fmt, ...) {
 }
 
 int g_num_sms = 148;
+
 
 static int bt_for(int B) {
   int bt = 1;
@@ -74,6 +78,11 @@ struct ctb_gpt {
   int mega_max_batch; // batches that use it (default 4: measured faster up to there; CTB_MEGA_MAX_BATCH overrides)
   unsigned* bar;     // its grid-barrier counter
   unsigned long long* trace;  // CTB_MEGA_TRACE=1: per-phase timestamps of the last step
+  bool flow_ok;      // dataflow decode step (flow.cuh), B <= 4: default back end for those batches
+  int flow_R;        // replicas of the broadcast exchange regions (CTB_FLOW_R)
+  unsigned long long* flow_arena;
+  unsigned* flow_epoch;
+  int steps_enqueued;  // loop iterations enqueued since ctb_gpt_begin (host-side bound for ctb_gpt_decode)
   float *tc_wqkv, *tc_wgu, *tc_heads_code, *tc_heads_text;  // permuted / norm-folded weight copies
   float *x_hi, *x_lo, *attn_hi, *attn_lo, *h_hi, *h_lo;      // [32][K] tf32-split activations
   CUtensorMap *m_wqkv, *m_wo, *m_wgu, *m_wd;                 // [layers] host arrays
@@ -158,9 +167,7 @@ static int encode_map_2d(CUtensorMap* m, const float* base, uint64_t rows, uint6
 
 template <int EPI, int NPAD, int CS>
 static int set_tc_attr() {
-  CTB_CUDA(cudaFuncSetAttribute(k_tc_dec<EPI, NPAD, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                TdCfg<NPAD>::SMEM_BYTES));
-  return CTB_OK;
+  return ensure_smem_attr((const void*)k_tc_dec<EPI, NPAD, CS>, TdCfg<NPAD>::SMEM_BYTES);
 }
 
 // cluster sizes of the split-K (K slices per 128-row tile)
@@ -269,6 +276,15 @@ extern "C" int ctb_gpt_create(const ctb_gpt_config* c, const float* weights_dev,
   TRY(dalloc(&h->st, 1));
   TRY(dalloc(&h->bar, 4));
   if (getenv("CTB_MEGA_TRACE")) TRY(dalloc(&h->trace, 256));
+  h->flow_ok = getenv("CTB_NO_FLOW") == nullptr && g_num_sms >= 128 && g_num_sms <= 191 && c->intermediate_size == 4 * KC &&
+               c->num_heads == c->num_kv_heads && c->num_heads * c->head_dim == KC && c->num_heads <= FL_HEADS;
+  if (h->flow_ok) {
+    TRY(dalloc(&h->flow_arena, FL_ARENA_WORDS));
+    TRY(dalloc(&h->flow_epoch, 4));
+    const unsigned e0 = FL_EPOCH_STEP;
+    cudaMemcpy(h->flow_epoch, &e0, sizeof(e0), cudaMemcpyHostToDevice);
+    h->flow_R = getenv("CTB_FLOW_R") ? std::max(1, std::min(FL_RMAX, atoi(getenv("CTB_FLOW_R")))) : 8;
+  }
 #undef TRY
   // static page assignment: row b owns pages [b*ppr, (b+1)*ppr); kernels only see the table
   std::vector<int> bt_host((size_t)c->max_batch * h->pages_per_row);
@@ -295,7 +311,7 @@ extern "C" int ctb_gpt_destroy(ctb_gpt* h) {
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   void* ptrs[] = {h->x, h->qbuf, h->attn, h->mlp, h->logits, h->kv, h->part, h->block_table, h->seq_len,
                   h->pos, h->counter, h->end_idx, h->idx, h->active, h->finish, h->st, h->tc_wqkv, h->tc_wgu,
-                  h->tc_heads_code, h->tc_heads_text, h->x_hi, h->x_lo, h->attn_hi, h->attn_lo, h->h_hi, h->h_lo, h->bar, h->trace, h->gw_hi, h->gw_lo, h->pf_resid, h->pf_xn, h->pf_qkv, h->pf_q,
+                  h->tc_heads_code, h->tc_heads_text, h->x_hi, h->x_lo, h->attn_hi, h->attn_lo, h->h_hi, h->h_lo, h->bar, h->trace, h->flow_arena, h->flow_epoch, h->gw_hi, h->gw_lo, h->pf_resid, h->pf_xn, h->pf_qkv, h->pf_q,
                   h->pf_attn, h->pf_gu, h->pf_h, h->pf_ones, h->pf_zeros, h->pf_npre, h->pf_nvalid};
   delete[] h->m_wqkv; delete[] h->m_wo; delete[] h->m_wgu; delete[] h->m_wd;
   for (void* p : ptrs) if (p) cudaFree(p);
@@ -307,11 +323,7 @@ extern "C" int ctb_gpt_destroy(ctb_gpt* h) {
 template <int BT, int EPI>
 static int launch_gemv_t(const GemvP& p, int ntiles, cudaStream_t s) {
   const size_t smem = (size_t)BT * KC * sizeof(float);
-  static bool attr_done = false;  // per instantiation
-  if (!attr_done) {
-    CTB_CUDA(cudaFuncSetAttribute(k_gemv<BT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
-  }
+  { int rc = ensure_smem_attr((const void*)k_gemv<BT, EPI>, (int)smem); if (rc) return rc; }
   // persistent: one CTA per SM strides over the warp tasks (DOWN: clusters of DOWN_SPLIT CTAs)
   int ctas = std::min(g_num_sms, (p.ntasks + GEMV_WARPS - 1) / GEMV_WARPS);
   unsigned cluster = 1;
@@ -345,11 +357,7 @@ static int launch_gemv(int bt, const GemvP& p, int ntiles, cudaStream_t s) {
 template <int BT>
 static int launch_gateup_small_t(const GemvP& p, cudaStream_t s) {
   const size_t smem = ((size_t)BT * KC + GU_ZONE_FLOATS) * sizeof(float);
-  static bool attr_done = false;
-  if (!attr_done) {
-    CTB_CUDA(cudaFuncSetAttribute(k_gateup_small<BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
-  }
+  { int rc = ensure_smem_attr((const void*)k_gateup_small<BT>, (int)smem); if (rc) return rc; }
   CTB_CUDA(launch_pdl(k_gateup_small<BT>, dim3(g_num_sms), dim3(GEMV_WARPS * 32), smem, s, p));
   CTB_LAUNCH_CHECK();
   return CTB_OK;
@@ -367,11 +375,7 @@ static int launch_gateup_small(int bt, const GemvP& p, cudaStream_t s) {
 template <int BT>
 static int launch_down_small_t(const GemvP& p, cudaStream_t s) {
   const size_t smem = (size_t)BT * p.K * sizeof(float);
-  static bool attr_done = false;
-  if (!attr_done) {
-    CTB_CUDA(cudaFuncSetAttribute(k_down_small<BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
-  }
+  { int rc = ensure_smem_attr((const void*)k_down_small<BT>, (int)smem); if (rc) return rc; }
   CTB_CUDA(launch_pdl(k_down_small<BT>, dim3(g_num_sms), dim3(GEMV_WARPS * 32), smem, s, p));
   CTB_LAUNCH_CHECK();
   return CTB_OK;
@@ -388,11 +392,7 @@ static int launch_down_small(int bt, const GemvP& p, cudaStream_t s) {
 
 static int launch_sample(const SampleP& sp, cudaStream_t s) {
   const size_t smem = (size_t)sp.V * sizeof(float) + 2 * 1024 * sizeof(uint32_t);
-  static size_t attr_max = 0;
-  if (smem > attr_max) {
-    CTB_CUDA(cudaFuncSetAttribute(k_sample, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_max = smem;
-  }
+  { int rc = ensure_smem_attr((const void*)k_sample, (int)smem); if (rc) return rc; }
   CTB_CUDA(launch_pdl(k_sample, dim3(sp.rows), dim3(SAMPLE_THREADS), smem, s, sp));
   CTB_LAUNCH_CHECK();
   return CTB_OK;
@@ -558,11 +558,7 @@ static int launch_step_mega_t(const MegaP& mp, cudaStream_t s) {
   // [BT][768] activations + the 144 KiB landing zone (gate/up weights; reused as merge scratch and for the down
   // phase's [BT][3072] activations)
   const size_t smem = (size_t)BT * KC * sizeof(float) + (size_t)MG_GW_FLOATS * sizeof(float);
-  static bool attr_done = false;
-  if (!attr_done) {
-    CTB_CUDA(cudaFuncSetAttribute(k_step<BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
-  }
+  { int rc = ensure_smem_attr((const void*)k_step<BT>, (int)smem); if (rc) return rc; }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(g_num_sms); cfg.blockDim = dim3(MG_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
   cudaLaunchAttribute attr[1];
@@ -602,6 +598,48 @@ static int launch_step_mega(ctb_gpt* h, int col, bool sample, cudaStream_t s) {
   }
 }
 
+template <int BT>
+static int launch_step_flow_t(const FlowP& fp, cudaStream_t s) {
+  const size_t smem = (size_t)FL_RING_BYTES + (size_t)BT * KC * sizeof(float);
+  { int rc = ensure_smem_attr((const void*)k_flow<BT>, (int)smem); if (rc) return rc; }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(g_num_sms); cfg.blockDim = dim3(FL_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;  // every CTA must be resident: CTAs wait for each other's words
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  CTB_CUDA(cudaLaunchKernelEx(&cfg, k_flow<BT>, fp));
+  CTB_LAUNCH_CHECK();
+  return CTB_OK;
+}
+
+static int launch_step_flow(ctb_gpt* h, int col, bool sample, cudaStream_t s) {
+  const ctb_gpt_config& c = h->cfg;
+  const ctb_gpt_layout& L = h->lay;
+  FlowP m{};
+  m.W = h->W; m.layer0 = L.layer0; m.layer_stride = L.layer_stride; m.o_wqkv = L.wqkv; m.o_wo = L.wo; m.o_wgu = L.wgate_up;
+  m.o_wd = L.wdown; m.o_ln1 = L.ln1; m.o_ln2 = L.ln2; m.o_final_norm = L.final_norm;
+  m.o_head = h->infer_text ? L.head_text : L.head_code; m.o_emb_code = L.emb_code; m.o_emb_text = L.emb_text;
+  m.o_cos = L.rope_cos; m.o_sin = L.rope_sin;
+  m.L = c.num_layers; m.I = c.intermediate_size; m.Hq = c.num_heads; m.hd = c.head_dim; m.eps = c.rms_eps;
+  m.scaling = 1.0f / sqrtf((float)c.head_dim);
+  m.logits = h->logits; m.kv = h->kv; m.kv_layer_floats = h->kv_layer_floats; m.block_table = h->block_table;
+  m.pages_per_row = h->pages_per_row; m.seq_len = h->seq_len; m.st = h->st;
+  m.decode = col < 0; m.col = col < 0 ? 0 : col; m.T0 = h->T0; m.sample = sample ? 1 : 0;
+  m.emb = h->emb; m.mask = h->mask; m.ids_out = h->ids_out; m.max_new = h->max_new; m.num_vq = c.num_vq;
+  m.num_audio = c.num_audio_tokens; m.infer_text = h->infer_text; m.B = h->B;
+  m.hidden_out = h->hiddens_out; m.hidden_stride = h->max_new * c.hidden_size;
+  m.rows_per_item = h->infer_text ? 1 : c.num_vq; m.V = h->infer_text ? c.num_text_tokens : c.num_audio_tokens;
+  m.arena = h->flow_arena; m.epoch = h->flow_epoch; m.R = h->flow_R; m.trace = h->trace;
+  switch (bt_for(h->B)) {
+    case 1: return launch_step_flow_t<1>(m, s);
+    case 2: return launch_step_flow_t<2>(m, s);
+    default: return launch_step_flow_t<4>(m, s);
+  }
+}
+
+static bool use_flow(const ctb_gpt* h) { return h->flow_ok && !h->use_tc && h->B <= FL_BMAX; }
+
 // One loop iteration.  col >= 0: prefill column `col` of the prompt; col < 0: decode step.
 // sample: run heads + sampler + finalize (last prompt column and every decode step).
 static int enqueue_step(ctb_gpt* h, int col, bool sample, cudaStream_t s) {
@@ -610,9 +648,9 @@ static int enqueue_step(ctb_gpt* h, int col, bool sample, cudaStream_t s) {
   const int decode = col < 0;
   int rc;
 
-  if (h->mega_ok && !h->use_tc && h->B <= h->mega_max_batch) {
+  if (use_flow(h) || (h->mega_ok && !h->use_tc && h->B <= h->mega_max_batch)) {
     // small batches: the whole step (input -> 20 layers -> heads) is one persistent cooperative kernel
-    if ((rc = launch_step_mega(h, col, sample, s))) return rc;
+    if ((rc = use_flow(h) ? launch_step_flow(h, col, sample, s) : launch_step_mega(h, col, sample, s))) return rc;
     if (!sample) return CTB_OK;
     const StepCtx xm = make_ctx(h, decode);
     if ((rc = launch_sampler(h, xm, s))) return rc;
@@ -667,6 +705,10 @@ extern "C" int ctb_gpt_profile_kernel(ctb_gpt* h, int32_t kind, void* stream) {
   if (kind == 5) return h->use_tc ? launch_heads_tc(h, s) : launch_heads(h, x, s);
   if (kind == 6) return launch_sampler(h, x, s);
   if (kind == 7) {  // the one-kernel decode step alone (context grows by one token per call)
+    if (h->steps_enqueued >= h->max_new || h->T0 + h->steps_enqueued >= h->cfg.max_context)
+      return set_err(CTB_ERR_STATE, "no room for another step (max_new / max_context reached)");
+    h->steps_enqueued++;
+    if (use_flow(h)) return launch_step_flow(h, -1, true, s);
     if (!(h->mega_ok && h->B <= 8)) return set_err(CTB_ERR_STATE, "one-kernel step unavailable for this handle/batch");
     return launch_step_mega(h, -1, true, s);
   }
@@ -774,6 +816,7 @@ extern "C" int ctb_gpt_begin(ctb_gpt* h, int32_t B, int32_t T0, const float* emb
   if (T0 < 1 || max_new_token < 1 || T0 + max_new_token > h->cfg.max_context)
     return set_err(CTB_ERR_ARG, "T0=%d + max_new=%d exceeds max_context=%d", T0, max_new_token, h->cfg.max_context);
   if (sampler->past_window > 31 || sampler->past_window < 0) return set_err(CTB_ERR_ARG, "past_window out of range");
+  if (sampler->min_tokens_to_keep < 1) return set_err(CTB_ERR_ARG, "min_tokens_to_keep must be >= 1");
   cudaStream_t s = (cudaStream_t)stream;
   h->B = B; h->T0 = T0; h->max_new = max_new_token; h->infer_text = infer_text ? 1 : 0;
   h->use_tc = h->tc_ready && B >= h->tc_min_batch;
@@ -805,6 +848,7 @@ extern "C" int ctb_gpt_begin(ctb_gpt* h, int32_t B, int32_t T0, const float* emb
       if ((rc = enqueue_step(h, col, col == T0 - 1, s))) return rc;
   }
   h->started = 1;
+  h->steps_enqueued = 1;
   return CTB_OK;
 }
 
@@ -812,6 +856,10 @@ extern "C" int ctb_gpt_decode(ctb_gpt* h, int32_t n_steps, void* stream) {
   if (!h || !h->started) return set_err(CTB_ERR_STATE, "ctb_gpt_begin has not been called");
   cudaStream_t s = (cudaStream_t)stream;
   int rc;
+  // ids_out / hiddens_out hold max_new steps and the KV pages max_context tokens: never enqueue past either
+  n_steps = std::min(n_steps, h->max_new - h->steps_enqueued);
+  if (n_steps <= 0) return CTB_OK;
+  h->steps_enqueued += n_steps;
   if (h->use_graph && !h->graph_exec) {
     // capture on a private stream (the caller's may be the legacy default stream, which cannot
     // be captured); the instantiated graph is then launched on the caller's stream
@@ -891,6 +939,8 @@ extern "C" int ctb_gpt_status_query(ctb_gpt* h, ctb_gpt_status* out, int32_t* en
   if (end_idx_host) CTB_CUDA(cudaMemcpyAsync(end_idx_host, h->end_idx, sizeof(int) * h->B, cudaMemcpyDeviceToHost, s));
   if (finish_host) CTB_CUDA(cudaMemcpyAsync(finish_host, h->finish, h->B, cudaMemcpyDeviceToHost, s));
   CTB_CUDA(cudaStreamSynchronize(s));
+  if (st.err != 0)
+    return set_err(CTB_ERR_STATE, "decode kernel reported error 0x%x (watchdog: a cross-CTA wait never completed)", st.err);
   out->steps_done = st.step;
   out->all_finished = st.all_finished;
   out->any_finished_first_step = st.any_first;
@@ -905,6 +955,8 @@ extern "C" int ctb_sample(const float* logits_dev, int32_t rows, int32_t V, int3
   if (rows < 1 || V < 1 || rows_per_item < 1 || rows % rows_per_item) return set_err(CTB_ERR_ARG, "bad shape");
   if ((size_t)V * 4 + 8192 > 200 * 1024) return set_err(CTB_ERR_ARG, "V=%d too large for the sampler", V);
   if (sampler->penalty_on && n_gen > 0 && !gen_ids_dev) return set_err(CTB_ERR_ARG, "gen_ids required");
+  if (sampler->past_window > 31 || sampler->past_window < 0) return set_err(CTB_ERR_ARG, "past_window out of range");
+  if (sampler->min_tokens_to_keep < 1) return set_err(CTB_ERR_ARG, "min_tokens_to_keep must be >= 1");
   SampleP sp{};
   sp.st = nullptr; sp.check_finished = 0; sp.logits = logits_dev; sp.rows = rows; sp.V = V;
   sp.rows_per_item = rows_per_item; sp.cfg = *sampler; sp.q_noise = q_noise_dev; sp.gen_ids = gen_ids_dev;

@@ -17,6 +17,7 @@ struct LoopState {
   int all_finished;    // finish.all()
   int any_first;       // i == 0 and finish.any()
   int n_gen;           // tokens appended to ids_out so far
+  int err;             // != 0: a device-side watchdog fired (flow.cuh); reported by ctb_gpt_status_query
 };
 
 constexpr int KC = 768;        // K chunk staged in shared memory (= hidden size of the model)

@@ -211,11 +211,7 @@ template <int EPI>
 inline int tc_gemm_launch(cudaStream_t s, const float* A, int lda, int B, int F, int N, int K, int taps, int Cin, int dil,
                           int pad, const float* W_hi, const float* W_lo, const float* bias, const float* gamma,
                           const float* res, int ldres, float* C, int ldc) {
-  static bool attr_done = false;
-  if (!attr_done) {
-    CTB_CUDA(cudaFuncSetAttribute(k_tc_gemm<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-    attr_done = true;
-  }
+  { int arc = ensure_smem_attr((const void*)k_tc_gemm<EPI>, TC_SMEM_BYTES); if (arc) return arc; }
   CUtensorMap ma, mh, ml;
   const cuuint64_t adims[3] = {(cuuint64_t)lda, (cuuint64_t)F, (cuuint64_t)B};
   const cuuint64_t astr[2] = {(cuuint64_t)lda * 4, (cuuint64_t)F * lda * 4};
