@@ -31,7 +31,7 @@ constexpr int FL_SLOTS = 4;
 constexpr int FL_SLOT_BYTES = 6144;
 constexpr int FL_SLOT_FLOATS = FL_SLOT_BYTES / 4;
 constexpr int FL_RING_BYTES = FL_WARPS * FL_SLOTS * FL_SLOT_BYTES;  // 192 KiB
-constexpr int FL_SMAX = 12;  // attention splits per (row, head)
+constexpr int FL_SMAX = 6;   // attention splits per (row, head): bounds the fan-in (and code size) of the merge in the O-proj phase
 constexpr int FL_CH = 64;    // keys per attention chunk: 8 per warp
 constexpr int FL_PW = 66;    // words of one attention partial: o[64], m, l
 constexpr int FL_BMAX = 4;   // batch rows the exchange arena is sized for
@@ -80,17 +80,20 @@ struct FlowP {
 };
 
 // ---------------------------------------------------------------- LL words
+// Stores are relaxed.gpu 64-bit (single-copy atomic: value and tag can never be seen torn).  Polls use ld.global.cg
+// (L2-coherent, never served from L1): a probe inside the running kernel measured 280 cycles per dependent .cg load
+// against 450 for ld.relaxed.gpu and 650 for ld.volatile, and the poll period is what an edge's latency is made of.
 __device__ __forceinline__ void ll_st(unsigned long long* p, float v, uint32_t tag) {
   const unsigned long long x = ((unsigned long long)tag << 32) | (unsigned long long)__float_as_uint(v);
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(x) : "memory");
 }
 __device__ __forceinline__ unsigned long long ll_ld(const unsigned long long* p) {
   unsigned long long x;
-  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(x) : "l"(p) : "memory");
+  asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(x) : "l"(p) : "memory");
   return x;
 }
 __device__ __forceinline__ void ll_ld2(const unsigned long long* p, unsigned long long& a, unsigned long long& b) {
-  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+  asm volatile("ld.global.cg.v2.u64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
 }
 __device__ __forceinline__ uint32_t ll_tag(unsigned long long x) { return (uint32_t)(x >> 32); }
 __device__ __forceinline__ float ll_val(unsigned long long x) { return __uint_as_float((uint32_t)x); }
@@ -119,6 +122,13 @@ __device__ __forceinline__ void fl_bulk(uint32_t dst, const void* src, uint32_t 
       "l"(src), "r"(bytes), "r"(bar), "l"(pol)
       : "memory");
 }
+// One elected lane of a converged warp (the pattern ptxas recognises: the guarded TMA instructions take their operands
+// through plain R2UR instead of a per-lane waterfall loop, which `lane == 0` produced).
+__device__ __forceinline__ bool fl_elect() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fl_expect(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
@@ -129,7 +139,8 @@ __device__ __forceinline__ bool fl_try_wait(uint32_t bar, uint32_t parity) {
   return ok != 0;
 }
 
-// Geometry every thread of a CTA agrees on (registers; uniform per warp).
+// Geometry every thread of a CTA agrees on.  The CTA-uniform part sits in shared memory (read by the non-inlined
+// issue routine); warp / lane / gw are recomputed from threadIdx where needed.
 struct FlowGeo {
   int G, NW, gw, cta, warp, lane;
   int S;                                // attention splits per (row, head)
@@ -162,106 +173,146 @@ __device__ __forceinline__ void fl_qkv_rows(const FlowP& p, int task, int& r0, i
   r1 = r0 + half;
 }
 
-// Issue side: position in the warp's task sequence.
+// Issue side.  The task sequence of a warp is the same in every layer (only the layer base moves), so it is tabulated
+// once per launch in shared memory: entry = {offset of copy 0 (floats, relative to the layer's weight / KV base),
+// stride between copies (floats), bytes per copy | ncopy << 16 | kind << 20}.  Issuing task n + FL_SLOTS after task n
+// is then a table lookup - the first version recomputed the sequence position with ~200 dependent integer
+// instructions per task and spent a quarter of the step there.
+constexpr int FL_TMAX = 40;  // table entries per warp: 2 (QKV) + K/V chunks + 1 (O) + 3 (gate/up) + 2 (down)
 struct FlowIss {
-  int l, st, sub, n;
+  int l, k, n, ntab, hsub;  // layer, entry within the layer, tasks issued so far, entries per layer, heads sub-iterator
 };
 
-// Find the next task at or after `it`, post its bulk copies into slot it.n % FL_SLOTS (lane 0) and advance.
-__device__ __forceinline__ void fl_issue(const FlowP& p, const FlowGeo& g, FlowIss& it, uint32_t ring, uint32_t bars,
-                                         uint64_t pol_w, uint64_t pol_kv) {
-  const float* src[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  int bytes = 0, ncopy = 0;
-  bool kvtask = false;
-  while (ncopy == 0) {
-    if (it.l < p.L) {
-      const float* Wl = p.W + p.layer0 + (int64_t)it.l * p.layer_stride;
-      const int st = it.st;
-      if (st == FS_KV) {
-        int chunk;
-        if (!fl_kv_more(g, it.sub, chunk)) { it.st = FS_O; it.sub = 0; continue; }
-        it.sub++;
-        if (!fl_kv_valid(g, chunk)) continue;
-        const int t0 = FL_CH * chunk + 8 * g.warp;
-        const int page = __ldg(p.block_table + g.u_b * p.pages_per_row + t0 / kPageTokens);
-        const float* kvl = p.kv + (size_t)it.l * p.kv_layer_floats;
-        src[0] = kvl + kv_off(page, 0, g.u_h, t0 % kPageTokens, p.Hq, p.hd);
-        src[1] = kvl + kv_off(page, 1, g.u_h, t0 % kPageTokens, p.Hq, p.hd);
-        bytes = 8 * 64 * 4; ncopy = 2; kvtask = true;
-        continue;
-      }
-      if (st == FS_Q0 || st == FS_Q1) {
-        const int j = st - FS_Q0;
-        if (fl_q_valid(g, j)) {
-          int r0, r1;
-          fl_qkv_rows(p, g.gw + j * g.NW, r0, r1);
-          src[0] = Wl + p.o_wqkv + (size_t)r0 * KC; src[1] = Wl + p.o_wqkv + (size_t)r1 * KC;
-          bytes = KC * 4; ncopy = 2;
-        }
-      } else if (st == FS_O) {
-        if (fl_o_valid(g)) { src[0] = Wl + p.o_wo + (size_t)(g.cta + g.G * g.warp) * KC; bytes = KC * 4; ncopy = 1; }
-      } else if (st <= FS_GU2) {
-        const int j = st - FS_GU0;
-        if (fl_gu_valid(g, j, p.I)) {
-          const int t = g.gw + j * g.NW;
-          src[0] = Wl + p.o_wgu + (size_t)t * KC; src[1] = Wl + p.o_wgu + (size_t)(p.I + t) * KC;
-          bytes = KC * 4; ncopy = 2;
-        }
-      } else {  // FS_D0 / FS_D1: this warp's 384-column slice of the CTA's down rows
-        const int j0 = st == FS_D0 ? 0 : 4, j1 = st == FS_D0 ? 4 : FL_ROWS;
-        const int nr = fl_d_rows(g, j0, j1);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (k < nr) src[k] = Wl + p.o_wd + (size_t)(g.cta + g.G * (j0 + k)) * p.I + g.warp * (p.I / FL_WARPS);
-        bytes = (p.I / FL_WARPS) * 4; ncopy = nr;
-      }
-      it.st = st + 1;
-      if (it.st == FS_NLAYER) { it.st = 0; it.l++; }
-    } else {
-      if (!fl_h_valid(g, it.sub)) return;  // end of the sequence
-      const int t = g.gw + it.sub * g.NW, nrows = p.rows_per_item * p.V;
-      src[0] = p.W + p.o_head + (size_t)(2 * t) * KC; src[1] = p.W + p.o_head + (size_t)min(2 * t + 1, nrows - 1) * KC;
-      bytes = KC * 4; ncopy = 2;
-      it.sub++;
+// Build this warp's per-layer table (all lanes execute it uniformly; lane 0 stores).  Returns the entry count.
+__device__ __noinline__ int fl_build_table(const FlowP& p, const FlowGeo* gs, int4* tab) {
+  FlowGeo g = *gs;
+  g.warp = threadIdx.x >> 5; g.lane = threadIdx.x & 31; g.gw = g.cta * FL_WARPS + g.warp;
+  int n = 0;
+  auto put = [&](int64_t off0, int64_t stride, int bytes, int ncopy, int kind) {
+    if (g.lane == 0 && n < FL_TMAX) tab[n] = make_int4((int)off0, (int)stride, bytes | (ncopy << 16) | (kind << 20), 0);
+    n++;
+  };
+  for (int j = 0; j < FL_QR; ++j)
+    if (fl_q_valid(g, j)) {
+      int r0, r1;
+      fl_qkv_rows(p, g.gw + j * g.NW, r0, r1);
+      put(p.o_wqkv + (int64_t)r0 * KC, (int64_t)(r1 - r0) * KC, KC * 4, 2, 0);
     }
+  for (int sub = 0;; ++sub) {
+    int chunk;
+    if (!fl_kv_more(g, sub, chunk)) break;
+    if (!fl_kv_valid(g, chunk)) continue;
+    const int t0 = FL_CH * chunk + 8 * g.warp;
+    const int page = __ldg(p.block_table + g.u_b * p.pages_per_row + t0 / kPageTokens);
+    const int64_t k0 = (int64_t)kv_off(page, 0, g.u_h, t0 % kPageTokens, p.Hq, p.hd);
+    const int64_t v0 = (int64_t)kv_off(page, 1, g.u_h, t0 % kPageTokens, p.Hq, p.hd);
+    put(k0, v0 - k0, 8 * 64 * 4, 2, 1);
   }
-  if (g.lane == 0) {
-    const int slot = it.n % FL_SLOTS;
-    const uint32_t bar = bars + slot * 8, dst = ring + slot * FL_SLOT_BYTES;
-    fl_expect(bar, (uint32_t)(bytes * ncopy));
-#pragma unroll
-    for (int k = 0; k < 6; ++k)
-      if (k < ncopy) fl_bulk(dst + k * bytes, src[k], (uint32_t)bytes, bar, kvtask ? pol_kv : pol_w);
+  if (fl_o_valid(g)) put(p.o_wo + (int64_t)(g.cta + g.G * g.warp) * KC, 0, KC * 4, 1, 0);
+  for (int j = 0; j < FL_GU; ++j)
+    if (fl_gu_valid(g, j, p.I)) put(p.o_wgu + (int64_t)(g.gw + j * g.NW) * KC, (int64_t)p.I * KC, KC * 4, 2, 0);
+  for (int half = 0; half < 2; ++half) {
+    const int j0 = half ? 4 : 0, j1 = half ? FL_ROWS : 4;
+    const int nr = fl_d_rows(g, j0, j1);
+    if (nr > 0)
+      put(p.o_wd + (int64_t)(g.cta + g.G * j0) * p.I + g.warp * (p.I / FL_WARPS), (int64_t)g.G * p.I, (p.I / FL_WARPS) * 4, nr, 0);
   }
-  it.n++;
+  return n;
 }
 
-// Consume side of the ring.
-struct FlowRing {
+// heads tasks (after the last layer): rare, computed directly
+__device__ __noinline__ void fl_issue_heads(const FlowP& p, const FlowGeo* gs, int hsub, uint32_t dst, uint32_t bar, uint64_t pol_w) {
+  const int gw = gs->cta * FL_WARPS + (threadIdx.x >> 5);
+  const int t = gw + hsub * gs->NW, nrows = p.rows_per_item * p.V;
+  if (fl_elect()) {
+    fl_expect(bar, 2u * KC * 4u);
+    fl_bulk(dst, p.W + p.o_head + (size_t)(2 * t) * KC, KC * 4, bar, pol_w);
+    fl_bulk(dst + KC * 4, p.W + p.o_head + (size_t)min(2 * t + 1, nrows - 1) * KC, KC * 4, bar, pol_w);
+  }
+}
+
+// Post the bulk copies of the next task into slot it.n % FL_SLOTS (lane 0) and advance the iterator.
+__device__ __forceinline__ void fl_issue(const FlowP& p, const FlowGeo* gs, const int4* tab, FlowIss& it, uint32_t ring,
+                                         uint32_t bars, uint64_t pol_w, uint64_t pol_kv) {
+  const int slot = it.n % FL_SLOTS;
+  const uint32_t bar = bars + slot * 8, dst = ring + slot * FL_SLOT_BYTES;
+  if (it.l < p.L) {
+    const int4 e = tab[it.k];
+    if (fl_elect()) {
+      const int bytes = e.z & 0xffff, ncopy = (e.z >> 16) & 0xf, kind = e.z >> 20;
+      const float* src = (kind ? p.kv + (size_t)it.l * p.kv_layer_floats : p.W + p.layer0 + (int64_t)it.l * p.layer_stride) + e.x;
+      fl_expect(bar, (uint32_t)(bytes * ncopy));
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (k < ncopy) fl_bulk(dst + k * bytes, src + (int64_t)k * e.y, (uint32_t)bytes, bar, kind ? pol_kv : pol_w);
+    }
+    if (++it.k == it.ntab) { it.k = 0; it.l++; }
+    it.n++;
+  } else if (gs->cta * FL_WARPS + (int)(threadIdx.x >> 5) + it.hsub * gs->NW < gs->nheads_tasks) {
+    fl_issue_heads(p, gs, it.hsub, dst, bar, pol_w);
+    it.hsub++;
+    it.n++;
+  }
+}
+
+// Per-warp ring state.  Consumed slots are NOT refilled on the spot: posting the bulk copies of the next task costs
+// ~500 cycles (expect_tx + UBLKCP issue), which used to sit between a task's stores and the next poll.  The warp
+// only counts what it owes (`owed`) and pays while it is waiting anyway: every failed poll iteration posts one refill;
+// a wait on the ring first posts whatever the tasks it is about to consume need.
+struct FlowW {
   float* base;      // this warp's slots (generic pointer)
   uint32_t ring;    // same, shared-space address
   uint32_t bars;    // this warp's FL_SLOTS mbarriers
   int n;            // tasks consumed so far
+  int owed;         // consumed slots not yet refilled
+  FlowIss it;
+  const int4* tab;
+  const FlowGeo* gs;
+  uint64_t pol_w, pol_kv;
 };
-__device__ __forceinline__ const float* fl_ring_wait(FlowRing& r, FlowWd& wd) {
-  const int slot = r.n % FL_SLOTS;
-  const uint32_t parity = (uint32_t)(r.n / FL_SLOTS) & 1u;
+__device__ __forceinline__ void fl_refill(const FlowP& p, FlowW& w) {
+  if (w.owed > 0) {
+    __syncwarp();  // every lane's reads of the slot are complete before the async proxy overwrites it
+    fl_issue(p, w.gs, w.tab, w.it, w.ring, w.bars, w.pol_w, w.pol_kv);
+    w.owed--;
+  }
+}
+// tasks n .. n + cnt - 1 must have been posted: at most FL_SLOTS - cnt refills may be outstanding
+__device__ __forceinline__ void fl_ensure(const FlowP& p, FlowW& w, int cnt) {
+  while (w.owed > FL_SLOTS - cnt) fl_refill(p, w);
+}
+__device__ __forceinline__ const float* fl_ring_slot_at(const FlowW& w, int k) { return w.base + ((w.n + k) % FL_SLOTS) * FL_SLOT_FLOATS; }
+// wait for tasks n .. n + cnt - 1 (cnt <= 3) with the try_waits in flight together
+__device__ __forceinline__ void fl_ring_wait_n(const FlowP& p, FlowW& w, int cnt, FlowWd& wd) {
+  fl_ensure(p, w, cnt);
+  uint32_t bar[3], par[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int n = w.n + k;
+    bar[k] = w.bars + (n % FL_SLOTS) * 8;
+    par[k] = (uint32_t)(n / FL_SLOTS) & 1u;
+  }
   wd.spins = 0;
-  while (!fl_try_wait(r.bars + slot * 8, parity))
-    if (__any_sync(0xffffffffu, fl_giveup(wd, 0x100 + slot))) { wd.dead = 1; break; }
-  return r.base + slot * FL_SLOT_FLOATS;
+  while (true) {
+    bool ok[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) ok[k] = k < cnt ? fl_try_wait(bar[k], par[k]) : true;
+    if (ok[0] && ok[1] && ok[2]) break;
+    if (__any_sync(0xffffffffu, fl_giveup(wd, 0x120))) { wd.dead = 1; break; }
+  }
 }
-__device__ __forceinline__ void fl_ring_release(const FlowP& p, const FlowGeo& g, FlowRing& r, FlowIss& it, uint64_t pol_w,
-                                                uint64_t pol_kv) {
-  __syncwarp();  // every lane's reads of the slot are complete before the async proxy overwrites it
-  r.n++;
-  fl_issue(p, g, it, r.ring, r.bars, pol_w, pol_kv);
+__device__ __forceinline__ const float* fl_ring_wait(const FlowP& p, FlowW& w, FlowWd& wd) {
+  fl_ring_wait_n(p, w, 1, wd);
+  return fl_ring_slot_at(w, 0);
 }
+// Measured: paying the refills lazily inside the poll loops (one per failed poll) lengthens the poll period and made
+// the step 20-40 % slower; refilling eagerly AFTER the phase's stores is the better trade.
+__device__ __forceinline__ void fl_ring_release(const FlowP& p, FlowW& w) { w.n++; w.owed++; fl_refill(p, w); }
 
 // ---------------------------------------------------------------- phase helpers
 // Poll p.B x 768 LL words into xs (raw), zero rows >= B, block barrier.
 template <int BT>
-__device__ __forceinline__ void fl_stage768(const FlowP& p, const unsigned long long* src, uint32_t tag, float* xs, FlowWd& wd) {
+__device__ __forceinline__ void fl_stage768(const FlowP& p, const unsigned long long* src, uint32_t tag, float* xs, FlowWd& wd, FlowW& fw) {
   const int tid = threadIdx.x;
   unsigned long long v[BT][3];
   wd.spins = 0;
@@ -307,10 +358,10 @@ template <int BT>
 __device__ __forceinline__ void fl_norm(float (&x)[BT][24], const float4 (&nw)[6], float eps) {
 #pragma unroll
   for (int b = 0; b < BT; ++b) {
-    float ss = 0.f;
+    float s4[4] = {0.f, 0.f, 0.f, 0.f};  // four interleaved partial sums: 6-deep dependent chains instead of 24
 #pragma unroll
-    for (int j = 0; j < 24; ++j) ss = fmaf(x[b][j], x[b][j], ss);
-    ss = warp_sum(ss);
+    for (int j = 0; j < 24; ++j) s4[j & 3] = fmaf(x[b][j], x[b][j], s4[j & 3]);
+    float ss = warp_sum((s4[0] + s4[1]) + (s4[2] + s4[3]));
     const float rinv = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(__fdiv_rn(ss, (float)KC), eps)));
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
@@ -371,7 +422,7 @@ __device__ __forceinline__ void fl_bcast_store(unsigned long long* rep0, int R, 
 }
 
 template <int BT>
-__global__ void __launch_bounds__(FL_THREADS, 1) k_flow(const FlowP p) {
+__global__ void __launch_bounds__(FL_THREADS, 1) k_flow(const __grid_constant__ FlowP p) {
   extern __shared__ __align__(128) unsigned char fl_smem[];
   float* xs = reinterpret_cast<float*>(fl_smem + FL_RING_BYTES);  // [BT][768]
   __shared__ __align__(8) uint64_t s_bar[FL_WARPS * FL_SLOTS];
@@ -379,8 +430,12 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_flow(const FlowP p) {
   __shared__ float s_cos[BT * 64], s_sin[BT * 64];
   __shared__ float s_red[FL_ROWS][FL_WARPS][BT];
   __shared__ float s_ml[FL_HEADS * FL_SMAX * 2];
+  __shared__ float s_w[FL_HEADS * FL_SMAX], s_gl[FL_HEADS];
+  __shared__ float s_resd[FL_ROWS * BT];
   __shared__ float s_am[FL_WARPS], s_al[FL_WARPS];
   __shared__ __align__(16) float s_ao[FL_WARPS][64];
+  __shared__ FlowGeo s_geo;
+  __shared__ int4 s_tab[FL_WARPS][FL_TMAX];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int LPB = 32 / BT;
@@ -396,6 +451,11 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_flow(const FlowP p) {
   int tr = 0;
 #define FL_TRACE() do { if (p.trace && blockIdx.x == 0 && tid == 0) p.trace[tr++] = globaltimer_ns(); } while (0)
   FL_TRACE();
+  // per-CTA event stamps of one layer (profiling aid; trace[256 + cta * 16 + k])
+#define FL_EV(k) do { if (p.trace && l == 10 && tid == 0) p.trace[256 + blockIdx.x * 16 + (k)] = globaltimer_ns(); } while (0)
+
+  // cycle stamps inside one gate/up task and one down task of CTA 0 / warp 0 (profiling aid; trace[3000 + k])
+#define FL_CK(k) do { if (p.trace && l == 10 && tid == 0 && blockIdx.x == 0) p.trace[3000 + (k)] = (unsigned long long)clock64(); } while (0)
 
   // ---- positions / pages / RoPE rows of this step (k_input)
   if (tid < BT) {
@@ -427,14 +487,19 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_flow(const FlowP p) {
   uint64_t pol_w, pol_kv;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_w));
   asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_kv));
-  FlowRing ring;
-  ring.base = reinterpret_cast<float*>(fl_smem) + (size_t)warp * FL_SLOTS * FL_SLOT_FLOATS;
-  ring.ring = smem_u32(ring.base);
-  ring.bars = smem_u32(&s_bar[warp * FL_SLOTS]);
-  ring.n = 0;
-  FlowIss it{0, 0, 0, 0};
+  if (tid == 0) s_geo = g;
+  __syncthreads();
+  FlowW fw;
+  fw.base = reinterpret_cast<float*>(fl_smem) + (size_t)warp * FL_SLOTS * FL_SLOT_FLOATS;
+  fw.ring = smem_u32(fw.base);
+  fw.bars = smem_u32(&s_bar[warp * FL_SLOTS]);
+  fw.n = 0; fw.owed = 0;
+  fw.it = FlowIss{0, 0, 0, 0, 0};
+  fw.tab = s_tab[warp]; fw.gs = &s_geo; fw.pol_w = pol_w; fw.pol_kv = pol_kv;
+  fw.it.ntab = fl_build_table(p, &s_geo, s_tab[warp]);
+  __syncwarp();
 #pragma unroll 1
-  for (int k = 0; k < FL_SLOTS; ++k) fl_issue(p, g, it, ring.ring, ring.bars, pol_w, pol_kv);
+  for (int k = 0; k < FL_SLOTS; ++k) fl_issue(p, fw.gs, fw.tab, fw.it, fw.ring, fw.bars, pol_w, pol_kv);
 
   for (int i = tid; i < BT * 64; i += FL_THREADS) {  // RoPE rows of this step's positions (p.hd == 64)
     const int b = i / 64;
@@ -476,7 +541,9 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_flow(const FlowP p) {
     {
       float4 nw[6];
       fl_load_nw(Wl + p.o_ln1, nw, lane);
-      if (l > 0) fl_stage768<BT>(p, myr + FL_A_X, tagl + FT_X, xs, wd);
+      FL_EV(0);
+      if (l > 0) fl_stage768<BT>(p, myr + FL_A_X, tagl + FT_X, xs, wd, fw);
+      FL_EV(1);
       float x[BT][24];
       fl_load_x<BT>(xs, x, lane);
       // residual of this warp's O-proj row (raw x), kept for phase C
@@ -484,10 +551,11 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_flow(const FlowP p) {
       if (fl_o_valid(g)) res_o = xs[(lane / LPB) * KC + o_row];
       fl_norm<BT>(x, nw, p.eps);
       float res_keep = res_o;
-#pragma unroll
+#pragma unroll 1
       for (int j = 0; j < FL_QR; ++j) {
         if (!fl_q_valid(g, j)) continue;
-        const float* slot = fl_ring_wait(ring, wd);
+        const float* slot = fl_ring_wait(p, fw, wd);
+        FL_EV(2);
         float a0[BT], a1[BT];
         fl_dot2<BT>(slot, x, a0, a1, lane);
         warp_reduce_scatter<BT>(a0);
@@ -515,9 +583,10 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_flow(const FlowP p) {
             kd[jj] = o0; kd[jj + half] = o1;
           }
         }
-        fl_ring_release(p, g, ring, it, pol_w, pol_kv);
+        fl_ring_release(p, fw);
       }
       FL_TRACE();
+      FL_EV(3);
 
       // ============ B: attention (one unit per CTA: row, head, key split) ============
       if (g.u_on) {
@@ -541,12 +610,14 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_flow(const FlowP p) {
 #pragma unroll
           for (int k = 0; k < 8; ++k) q[k] = ll_val(w[k]);
         }
+        FL_EV(4);
         float M = -INFINITY, L = 0.f, O = 0.f;
+        int pend_kv = 0;
         for (int sb = 0;; ++sb) {
           int chunk;
           if (!fl_kv_more(g, sb, chunk)) break;
           const bool have = fl_kv_valid(g, chunk);
-          const float* slot = have ? fl_ring_wait(ring, wd) : nullptr;
+          const float* slot = have ? fl_ring_wait(p, fw, wd) : nullptr;
           const int tbase = chunk * FL_CH + warp * 8 + grp;
           float4 k0[2], k1[2], v0[2], v1[2];
 #pragma unroll
@@ -621,7 +692,11 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_flow(const FlowP p) {
             o[j] += __shfl_xor_sync(0xffffffffu, o[j], 8);
             o[j] += __shfl_xor_sync(0xffffffffu, o[j], 16);
           }
-          if (have) fl_ring_release(p, g, ring, it, pol_w, pol_kv);
+          if (have) {
+            int nxt;
+            if (fl_kv_more(g, sb + 1, nxt)) fl_ring_release(p, fw);
+            else pend_kv = 1;  // last chunk: refill after the partial has been stored
+          }
           __syncthreads();  // previous chunk's merge no longer reads s_ao / s_am / s_al
           if (lane < 8) {
             *reinterpret_cast<float4*>(&s_ao[warp][lane * 8]) = make_float4(o[0], o[1], o[2], o[3]);
@@ -652,111 +727,159 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_flow(const FlowP p) {
             if (tid == 0) { ll_st(d + 64, M, tagl + FT_P); ll_st(d + 65, L, tagl + FT_P); }
           }
         }
+        if (pend_kv) fl_ring_release(p, fw);
       }
       FL_TRACE();
+      FL_EV(5);
 
       // ============ C: merge the attention splits, O-proj + residual ============
       __syncthreads();  // xs (raw x) is no longer read by any warp of this CTA
-      for (int b = 0; b < p.B; ++b) {
-        if (!s_active[b]) {
-#pragma unroll
-          for (int k = 0; k < 3; ++k) xs[b * KC + tid + 256 * k] = 0.f;
-          continue;
-        }
-        const int n = s_pos[b] + 1;
-        const int ns = min((n + FL_CH - 1) / FL_CH, g.S);
-        const unsigned long long* P = myr + FL_A_P + (size_t)b * FL_HEADS * FL_SMAX * FL_PW;
+#pragma unroll 1
+      for (int b = 0; b < BT; ++b) {
+        const bool live = b < p.B && s_active[b];  // uniform over the CTA
+        const int ns = live ? min((s_pos[b] + FL_CH) / FL_CH, g.S) : 0;
         float ov[3][FL_SMAX];
-        wd.spins = 0;
-        while (true) {
-          bool ok = true;
+        if (live) {
+          const unsigned long long* P = myr + FL_A_P + (size_t)b * FL_HEADS * FL_SMAX * FL_PW;
+          wd.spins = 0;
+          while (true) {
+            bool ok = true;
 #pragma unroll
-          for (int k = 0; k < 3; ++k) {
-            const int c = tid + 256 * k, hh = c >> 6, dd = c & 63;
+            for (int k = 0; k < 3; ++k) {
+              const int c = tid + 256 * k, hh = c >> 6, dd = c & 63;
 #pragma unroll
-            for (int s = 0; s < FL_SMAX; ++s)
-              if (s < ns) {
-                const unsigned long long w = ll_ld(P + (size_t)(hh * FL_SMAX + s) * FL_PW + dd);
-                ok = ok && (ll_tag(w) == tagl + FT_P);
-                ov[k][s] = ll_val(w);
-              }
+              for (int sp = 0; sp < FL_SMAX; ++sp)
+                if (sp < ns) {
+                  const unsigned long long w = ll_ld(P + (size_t)(hh * FL_SMAX + sp) * FL_PW + dd);
+                  ok = ok && (ll_tag(w) == tagl + FT_P);
+                  ov[k][sp] = ll_val(w);
+                }
+            }
+            for (int i = tid; i < p.Hq * ns * 2; i += FL_THREADS) {
+              const int hh = i / (2 * ns), rem = i % (2 * ns), sp = rem >> 1, which = rem & 1;
+              const unsigned long long w = ll_ld(P + (size_t)(hh * FL_SMAX + sp) * FL_PW + 64 + which);
+              ok = ok && (ll_tag(w) == tagl + FT_P);
+              s_ml[(hh * FL_SMAX + sp) * 2 + which] = ll_val(w);
+            }
+            if (__syncthreads_and(ok)) break;
+            if (__syncthreads_or(fl_giveup(wd, 0x400))) { wd.dead = 1; break; }
           }
-          for (int i = tid; i < p.Hq * ns * 2; i += FL_THREADS) {
-            const int hh = i / (2 * ns), rem = i % (2 * ns), s = rem >> 1, which = rem & 1;
-            const unsigned long long w = ll_ld(P + (size_t)(hh * FL_SMAX + s) * FL_PW + 64 + which);
-            ok = ok && (ll_tag(w) == tagl + FT_P);
-            s_ml[(hh * FL_SMAX + s) * 2 + which] = ll_val(w);
+          if (tid < p.Hq) {  // softmax weights of the splits, once per head (same expressions / order as k_step's merge)
+            const float* ml = s_ml + tid * FL_SMAX * 2;
+            float GM = -INFINITY;
+            for (int sp = 0; sp < ns; ++sp) GM = fmaxf(GM, ml[2 * sp]);
+            float GL = 0.f;
+            for (int sp = 0; sp < ns; ++sp) {
+              const float w = expf(ml[2 * sp] - GM);
+              GL = fmaf(w, ml[2 * sp + 1], GL);
+              s_w[tid * FL_SMAX + sp] = w;
+            }
+            s_gl[tid] = GL;
           }
-          if (__syncthreads_and(ok)) break;
-          if (__syncthreads_or(fl_giveup(wd, 0x400))) { wd.dead = 1; break; }
+          __syncthreads();
         }
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
           const int c = tid + 256 * k, hh = c >> 6;
-          const float* ml = s_ml + hh * FL_SMAX * 2;
-          float GM = -INFINITY;
+          float v = 0.f;
+          if (live) {
+            float GO = 0.f;
 #pragma unroll
-          for (int s = 0; s < FL_SMAX; ++s)
-            if (s < ns) GM = fmaxf(GM, ml[2 * s]);
-          float GL = 0.f, GO = 0.f;
-#pragma unroll
-          for (int s = 0; s < FL_SMAX; ++s)
-            if (s < ns) {
-              const float w = expf(ml[2 * s] - GM);
-              GL = fmaf(w, ml[2 * s + 1], GL);
-              GO = fmaf(w, ov[k][s], GO);
-            }
-          xs[b * KC + c] = GO / GL;
+            for (int sp = 0; sp < FL_SMAX; ++sp)
+              if (sp < ns) GO = fmaf(s_w[hh * FL_SMAX + sp], ov[k][sp], GO);
+            v = GO / s_gl[hh];
+          }
+          xs[b * KC + c] = v;
         }
-        __syncthreads();  // s_ml is rewritten by the next row
-      }
-      for (int b = p.B; b < BT; ++b) {
-#pragma unroll
-        for (int k = 0; k < 3; ++k) xs[b * KC + tid + 256 * k] = 0.f;
       }
       __syncthreads();
+      FL_EV(6);
       if (fl_o_valid(g)) {
         fl_load_x<BT>(xs, x, lane);
-        const float* slot = fl_ring_wait(ring, wd);
+        const float* slot = fl_ring_wait(p, fw, wd);
+        FL_EV(7);
         float a0[BT];
         fl_dot1<BT>(slot, x, a0, lane);
         warp_reduce_scatter<BT>(a0);
         const float out = __fadd_rn(res_keep, a0[0]);
         fl_bcast_store<BT>(par, R, FL_A_XO + (size_t)(lane / LPB) * KC + o_row, out, tagl + FT_XO, p.B, lane);
-        fl_ring_release(p, g, ring, it, pol_w, pol_kv);
+        fl_ring_release(p, fw);
       }
       FL_TRACE();
+      FL_EV(8);
     }
 
     // ============ D: gate/up + SiLU * mul ============
-    float res_d = 0.f;
     {
       float4 nw[6];
       fl_load_nw(Wl + p.o_ln2, nw, lane);
       __syncthreads();  // every warp is done with xs (attention output)
-      fl_stage768<BT>(p, myr + FL_A_XO, tagl + FT_XO, xs, wd);
-      if (tid < FL_ROWS * BT) {  // residual of this thread's down-phase output element (raw x')
+      FL_CK(8);
+      fl_stage768<BT>(p, myr + FL_A_XO, tagl + FT_XO, xs, wd, fw);
+      FL_EV(9);
+      FL_CK(9);
+      if (tid < FL_ROWS * BT) {  // residual of the down-phase output elements (raw x')
         const int b = tid % BT, j = tid / BT, row = g.cta + g.G * j;
-        if (row < KC) res_d = xs[b * KC + row];
+        s_resd[tid] = row < KC ? xs[b * KC + row] : 0.f;
       }
       float x[BT][24];
       fl_load_x<BT>(xs, x, lane);
+      FL_CK(10);
       fl_norm<BT>(x, nw, p.eps);
+      FL_CK(11);
+      {
+        // all (<= 3) gate/up pair tasks of the warp at once: one pass over the activations, ONE butterfly for the six
+        // row sums, the slot refills issued after the stores (they cost ~500 cycles each and nothing waits for them)
+        int ngu = 0;
 #pragma unroll
-      for (int j = 0; j < FL_GU; ++j) {
-        if (!fl_gu_valid(g, j, p.I)) continue;
-        const float* slot = fl_ring_wait(ring, wd);
-        float a0[BT], a1[BT];
-        fl_dot2<BT>(slot, x, a0, a1, lane);
-        warp_reduce_scatter<BT>(a0);
-        warp_reduce_scatter<BT>(a1);
-        const float v0 = a0[0], v1 = a1[0];
-        const float sg = __fdiv_rn(v0, __fadd_rn(1.0f, expf(-v0)));
-        const float act = __fmul_rn(sg, v1);
-        fl_bcast_store<BT>(par, R, FL_A_ACT + (size_t)(lane / LPB) * p.I + (g.gw + j * g.NW), act, tagl + FT_ACT, p.B, lane);
-        fl_ring_release(p, g, ring, it, pol_w, pol_kv);
+        for (int j = 0; j < FL_GU; ++j) ngu += fl_gu_valid(g, j, p.I) ? 1 : 0;
+        FL_CK(0);
+        const float4* sl[FL_GU];
+#pragma unroll
+        for (int j = 0; j < FL_GU; ++j) sl[j] = reinterpret_cast<const float4*>(fl_ring_slot_at(fw, j)) + lane;
+        fl_ring_wait_n(p, fw, ngu, wd);
+        FL_CK(1);
+        float acc[8 * BT];
+#pragma unroll
+        for (int k = 0; k < 8 * BT; ++k) acc[k] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+#pragma unroll
+          for (int j = 0; j < FL_GU; ++j)
+            if (j < ngu) {
+              const float4 u = sl[j][i * 32], v = sl[j][KC / 4 + i * 32];
+#pragma unroll
+              for (int b = 0; b < BT; ++b) {
+                float& a0 = acc[(2 * j) * BT + b];
+                float& a1 = acc[(2 * j + 1) * BT + b];
+                a0 = fmaf(u.x, x[b][4 * i], a0); a0 = fmaf(u.y, x[b][4 * i + 1], a0);
+                a0 = fmaf(u.z, x[b][4 * i + 2], a0); a0 = fmaf(u.w, x[b][4 * i + 3], a0);
+                a1 = fmaf(v.x, x[b][4 * i], a1); a1 = fmaf(v.y, x[b][4 * i + 1], a1);
+                a1 = fmaf(v.z, x[b][4 * i + 2], a1); a1 = fmaf(v.w, x[b][4 * i + 3], a1);
+              }
+            }
+        }
+        FL_CK(2);
+        warp_reduce_scatter<8 * BT>(acc);
+        FL_CK(3);
+        // After the butterfly the 8 lanes [8j, 8j+8) hold task j: gate sums of the BT rows (LPV lanes each), then the up
+        // sums.  All 8 lanes compute the activation of "their" row; the 2*LPV lanes of a row share the replica stores.
+        constexpr int LPV = 32 / (8 * BT);
+        const int gl = lane & 7, b = (gl / LPV) % BT, base8 = lane & ~7;
+        const float gv = __shfl_sync(0xffffffffu, acc[0], base8 + b * LPV);
+        const float uv = __shfl_sync(0xffffffffu, acc[0], base8 + BT * LPV + b * LPV);
+        if ((lane >> 3) < ngu && b < p.B) {
+          const float sg = __fdiv_rn(gv, __fadd_rn(1.0f, expf(-gv)));
+          const float act = __fmul_rn(sg, uv);
+          unsigned long long* d = par + FL_A_ACT + (size_t)b * p.I + (g.gw + (lane >> 3) * g.NW);
+          for (int rr = (gl % LPV) + (gl >= BT * LPV ? LPV : 0); rr < R; rr += 2 * LPV) ll_st(d + (size_t)rr * FL_REP_STRIDE, act, tagl + FT_ACT);
+        }
+        FL_CK(5);
+        for (int j = 0; j < ngu; ++j) fl_ring_release(p, fw);
+        FL_CK(6);
       }
       FL_TRACE();
+      FL_EV(10);
     }
 
     // ============ E: down + residual (K = 3072 split over the 8 warps) ============
@@ -773,15 +896,21 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_flow(const FlowP p) {
             unsigned long long w[12];
             wd.spins = 0;
             while (true) {
-              bool ok = true;
+              // spin on the first two words only (148 x 8 warps polling 3 KiB each is 3.5 MB of L2 reads per round);
+              // every word is still validated by its own tag once the sentinels have arrived
+              ll_ld2(ap + lane * 4, w[0], w[1]);
+              if (__all_sync(0xffffffffu, ll_tag(w[0]) == tagl + FT_ACT && ll_tag(w[1]) == tagl + FT_ACT)) {
+                bool ok = true;
+                ll_ld2(ap + lane * 4 + 2, w[2], w[3]);
 #pragma unroll
-              for (int i = 0; i < 3; ++i) {
-                ll_ld2(ap + (i * 32 + lane) * 4, w[4 * i], w[4 * i + 1]);
-                ll_ld2(ap + (i * 32 + lane) * 4 + 2, w[4 * i + 2], w[4 * i + 3]);
+                for (int i = 1; i < 3; ++i) {
+                  ll_ld2(ap + (i * 32 + lane) * 4, w[4 * i], w[4 * i + 1]);
+                  ll_ld2(ap + (i * 32 + lane) * 4 + 2, w[4 * i + 2], w[4 * i + 3]);
+                }
+#pragma unroll
+                for (int k = 2; k < 12; ++k) ok = ok && (ll_tag(w[k]) == tagl + FT_ACT);
+                if (__all_sync(0xffffffffu, ok)) break;
               }
-#pragma unroll
-              for (int k = 0; k < 12; ++k) ok = ok && (ll_tag(w[k]) == tagl + FT_ACT);
-              if (__all_sync(0xffffffffu, ok)) break;
               if (__any_sync(0xffffffffu, fl_giveup(wd, 0x500))) { wd.dead = 1; break; }
             }
 #pragma unroll
@@ -789,46 +918,54 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_flow(const FlowP p) {
           }
         }
       }
+      FL_EV(11);
+      {
+        // both down tasks (<= 6 row slices) together, one butterfly, refills after the partial sums are in shared memory
+        const int nr0 = fl_d_rows(g, 0, 4), nr1 = fl_d_rows(g, 4, FL_ROWS);
+        const float* s0 = fl_ring_slot_at(fw, 0);
+        const float* s1 = nr1 > 0 ? fl_ring_slot_at(fw, 1) : s0;
+        fl_ring_wait_n(p, fw, nr1 > 0 ? 2 : 1, wd);
+        float acc[8 * BT];
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const int j0 = half ? 4 : 0, j1 = half ? FL_ROWS : 4;
-        const int nr = fl_d_rows(g, j0, j1);
-        if (nr == 0) continue;
-        const float* slot = fl_ring_wait(ring, wd);
+        for (int k = 0; k < 8 * BT; ++k) acc[k] = 0.f;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          if (k >= nr) break;
-          const float4* wr = reinterpret_cast<const float4*>(slot + k * (3072 / FL_WARPS)) + lane;
-          float acc[BT];
+        for (int i = 0; i < 3; ++i) {
 #pragma unroll
-          for (int b = 0; b < BT; ++b) acc[b] = 0.f;
+          for (int k = 0; k < FL_ROWS; ++k) {
+            const bool valid = k < 4 ? (k < nr0) : (k - 4 < nr1);
+            if (valid) {
+              const float4 u = (reinterpret_cast<const float4*>((k < 4 ? s0 : s1) + (k & 3) * (3072 / FL_WARPS)) + lane)[i * 32];
 #pragma unroll
-          for (int i = 0; i < 3; ++i) {
-            const float4 u = wr[i * 32];
-#pragma unroll
-            for (int b = 0; b < BT; ++b) {
-              acc[b] = fmaf(u.x, xd[b][4 * i], acc[b]); acc[b] = fmaf(u.y, xd[b][4 * i + 1], acc[b]);
-              acc[b] = fmaf(u.z, xd[b][4 * i + 2], acc[b]); acc[b] = fmaf(u.w, xd[b][4 * i + 3], acc[b]);
+              for (int b = 0; b < BT; ++b) {
+                float& a = acc[k * BT + b];
+                a = fmaf(u.x, xd[b][4 * i], a); a = fmaf(u.y, xd[b][4 * i + 1], a);
+                a = fmaf(u.z, xd[b][4 * i + 2], a); a = fmaf(u.w, xd[b][4 * i + 3], a);
+              }
             }
           }
-          warp_reduce_scatter<BT>(acc);
-          if ((lane % LPB) == 0) s_red[j0 + k][warp][lane / LPB] = acc[0];
         }
-        fl_ring_release(p, g, ring, it, pol_w, pol_kv);
+        warp_reduce_scatter<8 * BT>(acc);
+        constexpr int LPV = 32 / (8 * BT);
+        const int vi = lane / LPV, k = vi / BT, b = vi % BT;
+        if ((lane % LPV) == 0 && k < FL_ROWS) s_red[k][warp][b] = acc[0];
+        fl_ring_release(p, fw);
+        if (nr1 > 0) fl_ring_release(p, fw);
       }
+      FL_EV(12);
       __syncthreads();
-      if (tid < FL_ROWS * BT) {  // K slices summed in the order 0..7 (deterministic)
-        const int b = tid % BT, j = tid / BT, row = g.cta + g.G * j;
+      if (tid < FL_ROWS * BT * 8) {  // K slices summed in the order 0..7 (deterministic); 8 threads share an element's replicas
+        const int e = tid >> 3, b = e % BT, j = e / BT, row = g.cta + g.G * j;
         if (row < KC && b < p.B) {
           float v = s_red[j][0][b];
 #pragma unroll
           for (int w = 1; w < FL_WARPS; ++w) v = __fadd_rn(v, s_red[j][w][b]);
-          const float out = __fadd_rn(res_d, v);
-          for (int r = 0; r < R; ++r)
+          const float out = __fadd_rn(s_resd[e], v);
+          for (int r = tid & 7; r < R; r += 8)
             ll_st(parn + (size_t)r * FL_REP_STRIDE + FL_A_X + (size_t)b * KC + row, out, tagl + 8u + FT_X);
         }
       }
       FL_TRACE();
+      FL_EV(13);
     }
   }
 
@@ -838,7 +975,7 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_flow(const FlowP p) {
     float4 nw[6];
     fl_load_nw(p.W + p.o_final_norm, nw, lane);
     __syncthreads();
-    fl_stage768<BT>(p, myr + FL_A_X, base + 8u * (uint32_t)p.L + FT_X, xs, wd);
+    fl_stage768<BT>(p, myr + FL_A_X, base + 8u * (uint32_t)p.L + FT_X, xs, wd, fw);
     float x[BT][24];
     fl_load_x<BT>(xs, x, lane);
     fl_norm<BT>(x, nw, p.eps);
@@ -854,7 +991,7 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_flow(const FlowP p) {
     const int nrows = p.rows_per_item * p.V;
     for (int j = 0; fl_h_valid(g, j); ++j) {
       const int t = g.gw + j * g.NW;
-      const float* slot = fl_ring_wait(ring, wd);
+      const float* slot = fl_ring_wait(p, fw, wd);
       float a0[BT], a1[BT];
       fl_dot2<BT>(slot, x, a0, a1, lane);
       warp_reduce_scatter<BT>(a0);
@@ -868,7 +1005,7 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_flow(const FlowP p) {
           p.logits[((size_t)b * p.rows_per_item + q1) * p.V + c1] = a1[0];
         }
       }
-      fl_ring_release(p, g, ring, it, pol_w, pol_kv);
+      fl_ring_release(p, fw);
     }
   }
   FL_TRACE();
@@ -878,6 +1015,8 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_flow(const FlowP p) {
     if (tid == 0) *p.epoch = base + FL_EPOCH_STEP;
   }
 #undef FL_TRACE
+#undef FL_EV
+#undef FL_CK
 }
 
 }  // namespace ctb

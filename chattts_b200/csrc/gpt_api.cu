@@ -80,6 +80,7 @@ struct ctb_gpt {
   unsigned long long* trace;  // CTB_MEGA_TRACE=1: per-phase timestamps of the last step
   bool flow_ok;      // dataflow decode step (flow.cuh), B <= 4: default back end for those batches
   int flow_R;        // replicas of the broadcast exchange regions (CTB_FLOW_R)
+  int flow_max_batch; // batches that use it (CTB_FLOW_MAX_BATCH, default 2)
   unsigned long long* flow_arena;
   unsigned* flow_epoch;
   int steps_enqueued;  // loop iterations enqueued since ctb_gpt_begin (host-side bound for ctb_gpt_decode)
@@ -275,7 +276,7 @@ extern "C" int ctb_gpt_create(const ctb_gpt_config* c, const float* weights_dev,
   TRY(dalloc(&h->finish, Bp));
   TRY(dalloc(&h->st, 1));
   TRY(dalloc(&h->bar, 4));
-  if (getenv("CTB_MEGA_TRACE")) TRY(dalloc(&h->trace, 256));
+  if (getenv("CTB_MEGA_TRACE")) TRY(dalloc(&h->trace, 4096));
   h->flow_ok = getenv("CTB_NO_FLOW") == nullptr && g_num_sms >= 128 && g_num_sms <= 191 && c->intermediate_size == 4 * KC &&
                c->num_heads == c->num_kv_heads && c->num_heads * c->head_dim == KC && c->num_heads <= FL_HEADS;
   if (h->flow_ok) {
@@ -283,7 +284,10 @@ extern "C" int ctb_gpt_create(const ctb_gpt_config* c, const float* weights_dev,
     TRY(dalloc(&h->flow_epoch, 4));
     const unsigned e0 = FL_EPOCH_STEP;
     cudaMemcpy(h->flow_epoch, &e0, sizeof(e0), cudaMemcpyHostToDevice);
-    h->flow_R = getenv("CTB_FLOW_R") ? std::max(1, std::min(FL_RMAX, atoi(getenv("CTB_FLOW_R")))) : 8;
+    // measured on B200 (tools/flow_check.py): one copy of the exchange words is fastest (replicas multiply the 8-byte
+    // stores; the read hot-spot they were meant to relieve is the smaller effect), and the kernel wins up to B = 2
+    h->flow_R = getenv("CTB_FLOW_R") ? std::max(1, std::min(FL_RMAX, atoi(getenv("CTB_FLOW_R")))) : 1;
+    h->flow_max_batch = getenv("CTB_FLOW_MAX_BATCH") ? std::max(0, std::min(FL_BMAX, atoi(getenv("CTB_FLOW_MAX_BATCH")))) : 2;
   }
 #undef TRY
   // static page assignment: row b owns pages [b*ppr, (b+1)*ppr); kernels only see the table
@@ -638,7 +642,7 @@ static int launch_step_flow(ctb_gpt* h, int col, bool sample, cudaStream_t s) {
   }
 }
 
-static bool use_flow(const ctb_gpt* h) { return h->flow_ok && !h->use_tc && h->B <= FL_BMAX; }
+static bool use_flow(const ctb_gpt* h) { return h->flow_ok && !h->use_tc && h->B <= h->flow_max_batch; }
 
 // One loop iteration.  col >= 0: prefill column `col` of the prompt; col < 0: decode step.
 // sample: run heads + sampler + finalize (last prompt column and every decode step).
@@ -926,7 +930,7 @@ extern "C" int ctb_gpt_embed_prompt(ctb_gpt* h, const int64_t* ids_dev, const ui
 
 extern "C" int ctb_gpt_debug_trace(ctb_gpt* h, unsigned long long* host_out, int n) {
   if (!h || !h->trace) return set_err(CTB_ERR_STATE, "trace disabled (set CTB_MEGA_TRACE=1 before ctb_gpt_create)");
-  CTB_CUDA(cudaMemcpy(host_out, h->trace, sizeof(unsigned long long) * (size_t)std::min(n, 256), cudaMemcpyDeviceToHost));
+  CTB_CUDA(cudaMemcpy(host_out, h->trace, sizeof(unsigned long long) * (size_t)std::min(n, 4096), cudaMemcpyDeviceToHost));
   return CTB_OK;
 }
 

@@ -85,7 +85,7 @@ def main():
 
     lib = _lib.load()
     ref, embed = make({"CTB_NO_FLOW": "1"})
-    new, _ = make({})
+    new, _ = make({"CTB_FLOW_MAX_BATCH": "4"})
     ok = True
     for B in [int(x) for x in a.batches.split(",")]:
         lengths = [16, 5, 11, 9][:B]
@@ -111,14 +111,14 @@ def main():
 
     print(f"old k_step  B=1: {time_steps(ref, embed, 1, a.tokens):8.1f} us/step", flush=True)
     for R in [int(x) for x in a.sweep.split(",")]:
-        g, _ = make({"CTB_FLOW_R": str(R)})
+        g, _ = make({"CTB_FLOW_R": str(R), "CTB_FLOW_MAX_BATCH": "4"})
         t = {B: time_steps(g, embed, B, a.tokens) for B in (1, 2, 4)}
         print(f"flow R={R:2d}: " + "  ".join(f"B={B}: {t[B]:7.1f} us/step" for B in t), flush=True)
         del g
         torch.cuda.empty_cache()
 
     # per-phase trace of CTA 0 (last step)
-    tr, _ = make({"CTB_MEGA_TRACE": "1"})
+    tr, _ = make({"CTB_MEGA_TRACE": "1", "CTB_FLOW_R": "1"})
     time_steps(tr, embed, 1, 64, reps=1)
     buf = (C.c_ulonglong * 256)()
     _lib.check(lib.ctb_gpt_debug_trace(tr._handle, buf, 256))
@@ -130,6 +130,27 @@ def main():
     print("trace ns/phase (avg layers 2..19): " + "  ".join(f"{nm}={v:.0f}" for nm, v in zip(names, avg)),
           f" layer={sum(avg):.0f}  heads={t[101] - t[100]}  total={t[101] - t[0]}", flush=True)
     print("layer0:", per[0], "layer1:", per[1], flush=True)
+    # per-CTA event stamps of layer 10 (see FL_EV in flow.cuh)
+    buf2 = (C.c_ulonglong * 4096)()
+    _lib.check(lib.ctb_gpt_debug_trace(tr._handle, buf2, 4096))
+    import numpy as np
+    ev = np.array([[buf2[256 + c * 16 + k] for k in range(14)] for c in range(148)], dtype=np.int64)
+    t0 = ev[:, 0].min()
+    names = ["A.start", "X.staged", "Q.slot", "A.end", "q.arrived", "B.end", "C.merged", "O.slot", "C.end", "XO.staged",
+             "D.end", "ACT.polled", "E.partial", "E.end"]
+    print("layer-10 events, ns after the first CTA entered the layer: min / median / max over CTAs (0 = not recorded)")
+    for k, nm in enumerate(names):
+        col = ev[:, k]
+        col = col[col > 0] - t0
+        if len(col):
+            print(f"  {k:2d} {nm:11s} n={len(col):3d}  min={col.min():6d}  med={int(np.median(col)):6d}  max={col.max():6d}  argmax_cta={int(np.argmax(ev[:, k]))}")
+    ck = [int(buf2[3000 + k]) for k in range(12)]
+    print("  GU (all tasks) of CTA0/warp0, cycles: wait=%d dot=%d reduce=%d silu+store=%d release=%d | stage=%d load_x=%d norm=%d" % (
+        ck[1] - ck[0], ck[2] - ck[1], ck[3] - ck[2], ck[5] - ck[3], ck[6] - ck[5], ck[9] - ck[8], ck[10] - ck[9], ck[11] - ck[10]))
+    print("  L2 probe (cycles per 8 dependent loads): relaxed.gpu=%d ldcg=%d volatile=%d | 8 stores issue=%d" % tuple(int(buf2[3020 + k]) for k in range(4)))
+    print("  CTA 0:", (ev[0] - t0).tolist())
+    print("  CTA 100:", (ev[100] - t0).tolist())
+    print("  CTA 147:", (ev[147] - t0).tolist(), flush=True)
 
 
 if __name__ == "__main__":
