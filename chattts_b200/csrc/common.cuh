@@ -138,6 +138,21 @@ __device__ __forceinline__ void warp_reduce_scatter(float (&v)[N]) {
   for (; off > 0; off >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
 }
 
+// Philox4x32-10 (counter-based) Exp(1) noise for the unseeded path (manual_seed=None has no parity target)
+__device__ __forceinline__ float philox_exp1(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2) {
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  uint32_t x0 = c0, x1 = c1, x2 = c2, x3 = 0x9E3779B9u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t h0 = __umulhi(0xD2511F53u, x0), l0 = 0xD2511F53u * x0;
+    const uint32_t h1 = __umulhi(0xCD9E8D57u, x2), l1 = 0xCD9E8D57u * x2;
+    x0 = h1 ^ x1 ^ k0; x1 = l1; x2 = h0 ^ x3 ^ k1; x3 = l0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  const float u = ((x0 >> 8) + 1) * (1.0f / 16777216.0f);  // (0, 1]
+  return -logf(u);
+}
+
 // order-preserving map float -> uint32 (larger float => larger key; -inf smallest)
 __device__ __forceinline__ uint32_t float_key(float f) {
   uint32_t u = __float_as_uint(f);

@@ -47,15 +47,20 @@ constexpr int FL_A_X = 0;                                       // [BMAX][768]  
 constexpr int FL_A_XO = FL_A_X + FL_BMAX * KC;                  // [BMAX][768]  residual stream after O-proj
 constexpr int FL_A_ACT = FL_A_XO + FL_BMAX * KC;                // [BMAX][3072] silu(gate) * up
 constexpr int FL_A_P = FL_A_ACT + FL_BMAX * 4 * KC;             // [BMAX][12][SMAX][66] attention partials
-constexpr int FL_A_END = FL_A_P + FL_BMAX * FL_HEADS * FL_SMAX * FL_PW;
+constexpr int FL_A_AO = FL_A_P + FL_BMAX * FL_HEADS * FL_SMAX * FL_PW;  // [BMAX][768] merged attention output
+constexpr int FL_A_END = FL_A_AO + FL_BMAX * KC;
 constexpr int FL_REP_STRIDE = ((FL_A_END + 1023) / 1024) * 1024;
 constexpr int FL_A_Q = 0, FL_A_KN = FL_BMAX * KC, FL_A_VN = 2 * FL_BMAX * KC;
 constexpr int FL_QKV_WORDS = 3 * FL_BMAX * KC;
-constexpr size_t FL_PARITY_WORDS = (size_t)FL_RMAX * FL_REP_STRIDE + FL_QKV_WORDS;
+// in-kernel sampling (audio rows, V <= 1024): logits of the <= 16 (row, codebook) rows and the sampled ids
+constexpr int FL_SROWS = 16, FL_VPAD = 1024;
+constexpr int FL_A_LOGITS = FL_QKV_WORDS, FL_A_IDX = FL_A_LOGITS + FL_SROWS * FL_VPAD;
+constexpr int FL_TAIL_WORDS = FL_A_IDX + 64;
+constexpr size_t FL_PARITY_WORDS = (size_t)FL_RMAX * FL_REP_STRIDE + FL_TAIL_WORDS;
 constexpr size_t FL_ARENA_WORDS = 2 * FL_PARITY_WORDS;
 constexpr unsigned FL_EPOCH_STEP = 256;  // tags of one launch: base + 8 * layer + kind
 
-enum FlowTagKind { FT_X = 0, FT_QKV = 1, FT_P = 2, FT_XO = 3, FT_ACT = 4 };
+enum FlowTagKind { FT_X = 0, FT_QKV = 1, FT_P = 2, FT_XO = 3, FT_ACT = 4, FT_LOGITS = 5, FT_IDX = 6, FT_AO = 7 };
 enum FlowStage { FS_Q0 = 0, FS_Q1 = 1, FS_KV = 2, FS_O = 3, FS_GU0 = 4, FS_GU1 = 5, FS_GU2 = 6, FS_D0 = 7, FS_D1 = 8, FS_NLAYER = 9 };
 
 struct FlowP {
@@ -77,6 +82,14 @@ struct FlowP {
   unsigned* epoch;            // tag base of the next launch (advanced by CTA 0 at the end of every launch)
   int R;                      // replicas in use (1..FL_RMAX)
   unsigned long long* trace;  // optional globaltimer stamps of CTA 0 (1 + 5 * L + 1)
+  // ---- multi-step mode (decode, audio): the sampling tail and the finish bookkeeping run inside the kernel
+  int nsteps;                 // decode steps this launch runs (1 when ink == 0)
+  int ink;                    // 1: sample in the kernel (k_sample / k_finalize are not launched)
+  ctb_sampler_config samp;
+  const float* q_noise;       // [rows][V] Exp(1) noise or nullptr (device Philox)
+  uint8_t* finish;            // [B]
+  int* end_idx;               // [B]
+  int32_t* ids_w;             // ids_out, writable
 };
 
 // ---------------------------------------------------------------- LL words
@@ -312,7 +325,8 @@ __device__ __forceinline__ void fl_ring_release(const FlowP& p, FlowW& w) { w.n+
 // ---------------------------------------------------------------- phase helpers
 // Poll p.B x 768 LL words into xs (raw), zero rows >= B, block barrier.
 template <int BT>
-__device__ __forceinline__ void fl_stage768(const FlowP& p, const unsigned long long* src, uint32_t tag, float* xs, FlowWd& wd, FlowW& fw) {
+__device__ __forceinline__ void fl_stage768(const FlowP& p, const unsigned long long* src, uint32_t tag, float* xs, FlowWd& wd, FlowW& fw,
+                                            const int* rowmask = nullptr) {
   const int tid = threadIdx.x;
   unsigned long long v[BT][3];
   wd.spins = 0;
@@ -320,13 +334,13 @@ __device__ __forceinline__ void fl_stage768(const FlowP& p, const unsigned long 
     bool ok = true;
 #pragma unroll
     for (int b = 0; b < BT; ++b)
-      if (b < p.B) {
+      if (b < p.B && (rowmask == nullptr || rowmask[b])) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) v[b][k] = ll_ld(src + b * KC + tid + 256 * k);
       }
 #pragma unroll
     for (int b = 0; b < BT; ++b)
-      if (b < p.B) {
+      if (b < p.B && (rowmask == nullptr || rowmask[b])) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) ok = ok && (ll_tag(v[b][k]) == tag);
       }
@@ -336,7 +350,7 @@ __device__ __forceinline__ void fl_stage768(const FlowP& p, const unsigned long 
 #pragma unroll
   for (int b = 0; b < BT; ++b) {
 #pragma unroll
-    for (int k = 0; k < 3; ++k) xs[b * KC + tid + 256 * k] = b < p.B ? ll_val(v[b][k]) : 0.f;
+    for (int k = 0; k < 3; ++k) xs[b * KC + tid + 256 * k] = (b < p.B && (rowmask == nullptr || rowmask[b])) ? ll_val(v[b][k]) : 0.f;
   }
   __syncthreads();
 }
@@ -371,6 +385,20 @@ __device__ __forceinline__ void fl_norm(float (&x)[BT][24], const float4 (&nw)[6
       x[b][4 * i + 3] = __fmul_rn(nw[i].w, __fmul_rn(x[b][4 * i + 3], rinv));
     }
   }
+}
+// Norm weights come from HBM (they are part of the streamed blob) and the L1 returns loads in issue order: a register
+// load of them right before a poll made every X / XO edge wait for a DRAM round trip.  They are now fetched into shared
+// memory with cp.async half a layer ahead; this waits for the thread's own copies (the phase's barrier publishes them).
+__device__ __forceinline__ void fl_nw_fetch(float* dst, const float* src) {
+  if (threadIdx.x < KC / 4) cp_async16(dst + threadIdx.x * 4, src + threadIdx.x * 4);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+// groups complete in order; the attention / MLP halves always have exactly one younger fetch in flight behind the one they need
+__device__ __forceinline__ void fl_nw_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+__device__ __forceinline__ void fl_nw_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fl_load_nw_s(const float* s_nw, float4 (&nw)[6], int lane) {
+#pragma unroll
+  for (int i = 0; i < 6; ++i) nw[i] = reinterpret_cast<const float4*>(s_nw)[i * 32 + lane];
 }
 __device__ __forceinline__ void fl_load_nw(const float* normw, float4 (&nw)[6], int lane) {
 #pragma unroll
@@ -421,6 +449,241 @@ __device__ __forceinline__ void fl_bcast_store(unsigned long long* rep0, int R, 
     for (int r = lane % LPB; r < R; r += LPB) ll_st(rep0 + (size_t)r * FL_REP_STRIDE + idx, vb, tag);
 }
 
+// ---------------------------------------------------------------- in-kernel sampling tail (V <= 1024)
+// k_sample's arithmetic with 256 threads: thread t plays the virtual threads t, t + 256, t + 512, t + 768 of the
+// 1024-thread kernel (virtual warp = warp + 8k, same lane) and every double-precision sum runs over the virtual warps
+// in k_sample's order, so the sampled index is bit for bit the one k_sample returns (sampler.cu:63-268).
+struct FlowSamp {
+  float x[FL_VPAD];
+  uint32_t key[2][1024];
+  double redd[32];
+  int redi[8];
+  float redf[8];
+  float bv[8];
+  int bi[8];
+  int win[32];
+  uint32_t thr;
+  int out;
+};
+__device__ __forceinline__ double fl_vsum_d(const double (&v)[4], double* redd) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double r[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) r[k] = warp_sum_d(v[k]);
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) redd[warp + 8 * k] = r[k];
+  }
+  __syncthreads();
+  double t = 0.0;
+#pragma unroll 8
+  for (int w = 0; w < 32; ++w) t += redd[w];  // fixed order => deterministic
+  return t;
+}
+__device__ __forceinline__ float fl_bmax(float v, float* redf) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) redf[warp] = v;
+  __syncthreads();
+  float t = -INFINITY;
+#pragma unroll
+  for (int w = 0; w < FL_WARPS; ++w) t = fmaxf(t, redf[w]);
+  return t;
+}
+__device__ __forceinline__ int fl_bsum_i(int v, int* redi) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = __reduce_add_sync(0xffffffffu, v);
+  __syncthreads();
+  if (lane == 0) redi[warp] = v;
+  __syncthreads();
+  int t = 0;
+#pragma unroll
+  for (int w = 0; w < FL_WARPS; ++w) t += redi[w];
+  return t;
+}
+// bitonic sort of 1024 keys, ascending by virtual-thread index i = tid + 256 e; result left in key[] registers
+__device__ __forceinline__ void fl_bitonic1024(uint32_t (&key)[4], uint32_t* buf0, uint32_t* buf1) {
+  const int tid = threadIdx.x;
+  int sb = 0;
+#pragma unroll 1
+  for (int k = 2; k <= 1024; k <<= 1) {
+#pragma unroll 1
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= 256) {  // partner in the same thread
+        const bool up0 = ((tid) & k) == 0, up1 = ((tid + 256) & k) == 0, up2 = ((tid + 512) & k) == 0;
+        if (j == 256) {  // pairs (0,1), (2,3)
+          uint32_t lo = min(key[0], key[1]), hi = max(key[0], key[1]);
+          key[0] = up0 ? lo : hi; key[1] = up0 ? hi : lo;
+          lo = min(key[2], key[3]); hi = max(key[2], key[3]);
+          key[2] = up2 ? lo : hi; key[3] = up2 ? hi : lo;
+        } else {         // j == 512: pairs (0,2), (1,3)
+          uint32_t lo = min(key[0], key[2]), hi = max(key[0], key[2]);
+          key[0] = up0 ? lo : hi; key[2] = up0 ? hi : lo;
+          lo = min(key[1], key[3]); hi = max(key[1], key[3]);
+          key[1] = up1 ? lo : hi; key[3] = up1 ? hi : lo;
+        }
+        continue;
+      }
+      uint32_t other[4];
+      if (j >= 32) {
+        uint32_t* buf = sb ? buf1 : buf0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) buf[tid + 256 * e] = key[e];
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < 4; ++e) other[e] = buf[(tid + 256 * e) ^ j];
+        sb ^= 1;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) other[e] = __shfl_xor_sync(0xffffffffu, key[e], j);
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int i = tid + 256 * e;
+        const bool up = (i & k) == 0, lower = (i & j) == 0;
+        key[e] = (lower == up) ? min(key[e], other[e]) : max(key[e], other[e]);
+      }
+    }
+  }
+}
+
+// One logits row: sm.x[0..V) raw logits, sm.win[0..nwin) the repetition window.  Returns the sampled id (all threads).
+__device__ __noinline__ int fl_sample_row(const ctb_sampler_config& c, const float* q_noise, FlowSamp& sm, int V, int row, int qi,
+                                          int nwin, int step, unsigned long long* dbg) {
+  int dk = 0;
+#define FL_SK() do { if (dbg && threadIdx.x == 0) dbg[dk++] = (unsigned long long)clock64(); } while (0)
+  FL_SK();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool pen = c.penalty_on && row < c.penalty_max_ids;
+  const float temp = c.temperature[qi];
+  for (int v = tid; v < V; v += FL_THREADS) {
+    float x = __fdiv_rn(sm.x[v], temp);
+    if (pen) {
+      int cnt = 0;
+      for (int w = 0; w < nwin; ++w) cnt += (sm.win[w] == v);
+      const float a = c.penalty_lut[cnt];
+      x = (x < 0.f) ? __fmul_rn(x, a) : __fdiv_rn(x, a);
+    }
+    sm.x[v] = x;
+  }
+  __syncthreads();
+  float mx = -INFINITY;
+  for (int v = tid; v < V; v += FL_THREADS) mx = fmaxf(mx, sm.x[v]);
+  mx = fl_bmax(mx, sm.redf);
+  FL_SK();
+
+  const bool use_p = c.top_p >= 0.f;
+  const int kk = c.top_k > 0 ? min(max(c.top_k, c.min_tokens_to_keep), V) : 0;
+  const int min_keep = min(c.min_tokens_to_keep, V);
+  uint32_t thr_key = 0;
+  if (use_p || kk > 0) {
+    double den = 0.0;
+    if (use_p) {
+      double dv[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { const int vt = tid + 256 * k; dv[k] = vt < V ? (double)expf(sm.x[vt] - mx) : 0.0; }
+      den = fl_vsum_d(dv, sm.redd);
+    }
+    FL_SK();
+    const float denf = (float)den;
+    const float pthr = (float)(1.0 - (double)c.top_p);
+    uint32_t key[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const int vt = tid + 256 * k; key[k] = vt < V ? float_key(sm.x[vt]) : 0u; }
+    fl_bitonic1024(key, sm.key[0], sm.key[1]);
+    FL_SK();
+    __syncthreads();
+    uint32_t* skey = sm.key[0];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) skey[tid + 256 * k] = key[k];
+    __syncthreads();
+    uint32_t t_p = 0;
+    if (use_p) {
+      double inc[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t ky = key[k];
+        double a = ky ? (double)__fdiv_rn(expf(key_float(ky) - mx), denf) : 0.0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const double n = __shfl_up_sync(0xffffffffu, a, o);
+          if (lane >= o) a += n;
+        }
+        inc[k] = a;
+      }
+      __syncthreads();
+      if (lane == 31) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) sm.redd[warp + 8 * k] = inc[k];
+      }
+      __syncthreads();
+      int removed = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int vw = warp + 8 * k, vt = tid + 256 * k;
+        double base = 0.0;
+        for (int w = 0; w < vw; ++w) base += sm.redd[w];
+        const float cum = (float)(base + inc[k]);
+        removed += ((cum <= pthr) && (vt < 1024 - min_keep)) ? 1 : 0;
+      }
+      const int nrem = fl_bsum_i(removed, sm.redi);  // the removed set is a prefix of the sorted row
+      t_p = skey[nrem];
+      FL_SK();
+    }
+    const uint32_t t_k = kk > 0 ? skey[1024 - kk] : 0u;
+    thr_key = max(t_p, t_k);
+  }
+  if (c.greedy) {
+    float gm = -INFINITY;
+    for (int v = tid; v < V; v += FL_THREADS)
+      if (!(c.greedy == 2 && v == c.eos_token)) gm = fmaxf(gm, sm.x[v]);
+    gm = fl_bmax(gm, sm.redf);
+    thr_key = float_key(gm);
+  }
+  __syncthreads();  // every read of sm.key / sm.x above is complete
+  const bool ban = step < c.min_new_token;
+  float mx2 = -INFINITY;
+  for (int v = tid; v < V; v += FL_THREADS) {
+    float x = sm.x[v];
+    if (float_key(x) < thr_key || ((ban || c.greedy == 2) && v == c.eos_token)) x = -INFINITY;
+    sm.x[v] = x;
+    mx2 = fmaxf(mx2, x);
+  }
+  mx2 = fl_bmax(mx2, sm.redf);
+  double dv2[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { const int vt = tid + 256 * k; dv2[k] = vt < V ? (double)expf(sm.x[vt] - mx2) : 0.0; }
+  const float den2f = (float)fl_vsum_d(dv2, sm.redd);
+  FL_SK();
+  float best = -1.f;
+  int besti = 0x7fffffff;
+  for (int v = tid; v < V; v += FL_THREADS) {
+    const float pr = __fdiv_rn(expf(sm.x[v] - mx2), den2f);
+    const float qn = q_noise ? q_noise[(size_t)row * V + v] : philox_exp1(c.philox_seed, (uint32_t)row, (uint32_t)v, (uint32_t)step);
+    const float r = __fdiv_rn(pr, qn);
+    if (r > best) { best = r; besti = v; }  // ascending v within a thread: first max wins
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+    if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+  }
+  __syncthreads();
+  if (lane == 0) { sm.bv[warp] = best; sm.bi[warp] = besti; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < FL_WARPS; ++w)
+      if (sm.bv[w] > best || (sm.bv[w] == best && sm.bi[w] < besti)) { best = sm.bv[w]; besti = sm.bi[w]; }
+    sm.out = besti < V ? besti : 0;  // all-NaN row: ATen argmax returns the first index
+  }
+  __syncthreads();
+  FL_SK();
+#undef FL_SK
+  return sm.out;
+}
+
 template <int BT>
 __global__ void __launch_bounds__(FL_THREADS, 1) k_flow(const __grid_constant__ FlowP p) {
   extern __shared__ __align__(128) unsigned char fl_smem[];
@@ -429,13 +692,14 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_flow(const __grid_constant__ 
   __shared__ int s_pos[BT], s_active[BT], s_page[BT];
   __shared__ float s_cos[BT * 64], s_sin[BT * 64];
   __shared__ float s_red[FL_ROWS][FL_WARPS][BT];
-  __shared__ float s_ml[FL_HEADS * FL_SMAX * 2];
-  __shared__ float s_w[FL_HEADS * FL_SMAX], s_gl[FL_HEADS];
   __shared__ float s_resd[FL_ROWS * BT];
   __shared__ float s_am[FL_WARPS], s_al[FL_WARPS];
   __shared__ __align__(16) float s_ao[FL_WARPS][64];
   __shared__ FlowGeo s_geo;
+  __shared__ __align__(16) float s_nw1[KC], s_nw2[KC];  // RMSNorm weights of the coming attention / MLP half, fetched a phase early
   __shared__ int4 s_tab[FL_WARPS][FL_TMAX];
+  __shared__ FlowSamp s_samp_store[BT <= 2 ? 1 : 0 + (BT > 2)];
+  FlowSamp& s_samp = s_samp_store[0];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int LPB = 32 / BT;
@@ -446,18 +710,22 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_flow(const __grid_constant__ 
   pdl_wait();
   if (p.decode && ldg_cg(&p.st->all_finished)) return;  // uniform over the grid; nothing has been issued yet
 
+  constexpr bool INK = BT <= 2;  // in-kernel sampling is built for the batches this kernel is the default for
+  __shared__ int s_ids[BT * 8];       // ids sampled by the previous step (multi-step mode)
+  __shared__ int s_fin[BT], s_end[BT];
+  __shared__ int s_allfin;
   FlowWd wd{&p.st->err, 0, 0};
-  const uint32_t base = (uint32_t)ldg_cg(reinterpret_cast<const int*>(p.epoch));
+  uint32_t base = (uint32_t)ldg_cg(reinterpret_cast<const int*>(p.epoch));
   int tr = 0;
-#define FL_TRACE() do { if (p.trace && blockIdx.x == 0 && tid == 0) p.trace[tr++] = globaltimer_ns(); } while (0)
-  FL_TRACE();
+#define FL_TRACE() do { if (p.trace && blockIdx.x == 0 && tid == 0 && tr < 250) p.trace[tr++] = globaltimer_ns(); } while (0)
   // per-CTA event stamps of one layer (profiling aid; trace[256 + cta * 16 + k])
 #define FL_EV(k) do { if (p.trace && l == 10 && tid == 0) p.trace[256 + blockIdx.x * 16 + (k)] = globaltimer_ns(); } while (0)
-
-  // cycle stamps inside one gate/up task and one down task of CTA 0 / warp 0 (profiling aid; trace[3000 + k])
+  // cycle stamps inside the gate/up phase of CTA 0 / warp 0 (profiling aid; trace[3000 + k])
 #define FL_CK(k) do { if (p.trace && l == 10 && tid == 0 && blockIdx.x == 0) p.trace[3000 + (k)] = (unsigned long long)clock64(); } while (0)
 
-  // ---- positions / pages / RoPE rows of this step (k_input)
+  // ---- loop state of this launch
+  int ngen = p.decode ? ldg_cg(&p.st->n_gen) : 0;   // tokens appended to ids_out so far
+  int lstep = p.decode ? ldg_cg(&p.st->step) : 0;   // loop iterations completed (gpt.py: i)
   if (tid < BT) {
     int act = 0, pos = 0;
     if (tid < p.B) {
@@ -465,30 +733,15 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_flow(const __grid_constant__ 
       act = p.decode ? 1 : (p.mask[(size_t)tid * p.T0 + p.col] != 0);
     }
     s_pos[tid] = pos; s_active[tid] = act;
-    s_page[tid] = tid < p.B ? __ldg(p.block_table + tid * p.pages_per_row + pos / kPageTokens) : 0;
+    s_fin[tid] = (tid < p.B && p.ink) ? (int)p.finish[tid] : 0;
+    s_end[tid] = (tid < p.B && p.ink) ? ldg_cg(&p.end_idx[tid]) : 0;
   }
-  __syncthreads();
-
-  FlowGeo g;
-  g.G = gridDim.x; g.NW = g.G * FL_WARPS; g.cta = blockIdx.x; g.warp = warp; g.lane = lane; g.gw = g.cta * FL_WARPS + warp;
-  g.S = max(1, min(FL_SMAX, g.G / (p.Hq * p.B)));
-  {
-    const int u = g.cta;
-    g.u_on = 0; g.u_b = 0; g.u_h = 0; g.u_split = 0; g.u_n = 0; g.u_nchunk = 0;
-    if (u < p.B * p.Hq * g.S) {
-      g.u_split = u % g.S; g.u_h = (u / g.S) % p.Hq; g.u_b = u / (g.S * p.Hq);
-      g.u_n = s_pos[g.u_b] + 1;
-      g.u_nchunk = (g.u_n + FL_CH - 1) / FL_CH;
-      g.u_on = s_active[g.u_b] && g.u_split < min(g.u_nchunk, g.S);
-    }
-  }
-  g.nheads_tasks = p.sample ? (p.rows_per_item * p.V + 1) / 2 : 0;
-
+  const bool ink = INK && p.ink != 0;
+  const int nrows_s = p.B * p.rows_per_item;           // sampler rows (one CTA each)
+  const int R = p.R;
   uint64_t pol_w, pol_kv;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_w));
   asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_kv));
-  if (tid == 0) s_geo = g;
-  __syncthreads();
   FlowW fw;
   fw.base = reinterpret_cast<float*>(fl_smem) + (size_t)warp * FL_SLOTS * FL_SLOT_FLOATS;
   fw.ring = smem_u32(fw.base);
@@ -496,54 +749,114 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_flow(const __grid_constant__ 
   fw.n = 0; fw.owed = 0;
   fw.it = FlowIss{0, 0, 0, 0, 0};
   fw.tab = s_tab[warp]; fw.gs = &s_geo; fw.pol_w = pol_w; fw.pol_kv = pol_kv;
-  fw.it.ntab = fl_build_table(p, &s_geo, s_tab[warp]);
-  __syncwarp();
-#pragma unroll 1
-  for (int k = 0; k < FL_SLOTS; ++k) fl_issue(p, fw.gs, fw.tab, fw.it, fw.ring, fw.bars, pol_w, pol_kv);
+  FlowGeo g;
+  g.G = gridDim.x; g.NW = g.G * FL_WARPS; g.cta = blockIdx.x; g.warp = warp; g.lane = lane; g.gw = g.cta * FL_WARPS + warp;
+  g.S = max(1, min(FL_SMAX, g.G / (p.Hq * p.B)));
+  g.nheads_tasks = p.sample ? (p.rows_per_item * p.V + 1) / 2 : 0;
+  const int myrep = g.cta % R;
+  const int o_row = g.cta + g.G * warp;  // this warp's O-proj row (valid iff fl_o_valid)
+  unsigned long long* tailw = p.arena + (size_t)FL_RMAX * FL_REP_STRIDE;  // parity-0 tail: q/k/v words, logits, ids
+  __syncthreads();
 
-  for (int i = tid; i < BT * 64; i += FL_THREADS) {  // RoPE rows of this step's positions (p.hd == 64)
-    const int b = i / 64;
-    s_cos[i] = b < p.B ? __ldg(p.W + p.o_cos + (size_t)s_pos[b] * 64 + (i % 64)) : 0.f;
-    s_sin[i] = b < p.B ? __ldg(p.W + p.o_sin + (size_t)s_pos[b] * 64 + (i % 64)) : 0.f;
+  // the repetition window of this CTA's sampler row: the last <= past_window ids of (item, codebook)
+  int nwin = 0;
+  if constexpr (INK) {
+    if (ink && g.cta < nrows_s) {
+      const int item = g.cta / p.rows_per_item, qi = g.cta % p.rows_per_item;
+      const bool pen = p.samp.penalty_on && g.cta < p.samp.penalty_max_ids;
+      nwin = pen ? min(ngen, p.samp.past_window) : 0;
+      if (tid < nwin) s_samp.win[tid] = ldg_cg(&p.ids_out[((size_t)item * p.max_new + (ngen - nwin + tid)) * p.num_vq + qi]);
+    }
   }
-  const int ngen = p.decode ? ldg_cg(&p.st->n_gen) : 0;
-  for (int i = tid; i < BT * KC; i += FL_THREADS) {  // step input: prompt column or sum of the code embeddings
-    const int b = i / KC, k = i % KC;
-    float v = 0.f;
-    if (b < p.B) {
-      if (!p.decode) {
-        v = s_active[b] ? p.emb[((size_t)b * p.T0 + p.col) * KC + k] : 0.f;
-      } else {
-        const int32_t* id = p.ids_out + ((size_t)b * p.max_new + (ngen - 1)) * p.num_vq;
-        if (p.infer_text) {
-          v = p.W[p.o_emb_text + (size_t)ldg_cg(&id[0]) * KC + k];
+
+  // ---- pages / unit geometry / task table of a step's positions, first FL_SLOTS tasks posted (k_input).  Used before
+  // the loop and, for the NEXT step, before the sampling tail: the ring is idle then and the weights of layer 0 are in
+  // shared memory by the time the sampled ids arrive.
+#define FL_PREP_STEP()                                                                                                  \
+  do {                                                                                                                  \
+    if (tid < BT) s_page[tid] = tid < p.B ? __ldg(p.block_table + tid * p.pages_per_row + s_pos[tid] / kPageTokens) : 0; \
+    {                                                                                                                   \
+      const int u = g.cta;                                                                                              \
+      g.u_on = 0; g.u_b = 0; g.u_h = 0; g.u_split = 0; g.u_n = 0; g.u_nchunk = 0;                                       \
+      if (u < p.B * p.Hq * g.S) {                                                                                       \
+        g.u_split = u % g.S; g.u_h = (u / g.S) % p.Hq; g.u_b = u / (g.S * p.Hq);                                        \
+        g.u_n = s_pos[g.u_b] + 1;                                                                                       \
+        g.u_nchunk = (g.u_n + FL_CH - 1) / FL_CH;                                                                       \
+        g.u_on = s_active[g.u_b] && g.u_split < min(g.u_nchunk, g.S);                                                   \
+      }                                                                                                                 \
+    }                                                                                                                   \
+    if (tid == 0) s_geo = g;                                                                                            \
+    __syncthreads();                                                                                                    \
+    fw.it.l = 0; fw.it.k = 0; fw.it.hsub = 0;                                                                           \
+    fw.it.ntab = fl_build_table(p, &s_geo, s_tab[warp]);                                                                \
+    __syncwarp();                                                                                                       \
+    for (int k_ = 0; k_ < FL_SLOTS; ++k_) fl_issue(p, fw.gs, fw.tab, fw.it, fw.ring, fw.bars, pol_w, pol_kv);           \
+    for (int i = tid; i < BT * 64; i += FL_THREADS) {                                                                   \
+      const int b = i / 64;                                                                                             \
+      s_cos[i] = b < p.B ? __ldg(p.W + p.o_cos + (size_t)s_pos[b] * 64 + (i % 64)) : 0.f;                               \
+      s_sin[i] = b < p.B ? __ldg(p.W + p.o_sin + (size_t)s_pos[b] * 64 + (i % 64)) : 0.f;                               \
+    }                                                                                                                   \
+  } while (0)
+
+  FL_PREP_STEP();
+  FL_TRACE();
+#pragma unroll 1
+  for (int sidx = 0;; ++sidx) {
+  // ======================================================================== one decode step
+  FL_TRACE();
+  fl_nw_fetch(s_nw1, p.W + p.layer0 + p.o_ln1);
+  fl_nw_fetch(s_nw2, p.W + p.layer0 + p.o_ln2);
+  {  // step input: prompt column or sum of the code embeddings; every load of the thread in flight together
+    float ev[BT * 3][8];
+#pragma unroll
+    for (int it_ = 0; it_ < BT * 3; ++it_) {
+      const int i = tid + it_ * FL_THREADS, b = i / KC, k = i % KC;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) ev[it_][q] = 0.f;
+      if (b < p.B) {
+        if (!p.decode) {
+          ev[it_][0] = s_active[b] ? p.emb[((size_t)b * p.T0 + p.col) * KC + k] : 0.f;
+        } else if (p.infer_text) {
+          const int id0 = ldg_cg(p.ids_out + ((size_t)b * p.max_new + (ngen - 1)) * p.num_vq);
+          ev[it_][0] = p.W[p.o_emb_text + (size_t)id0 * KC + k];
         } else {
-          for (int q = 0; q < p.num_vq; ++q) v += p.W[p.o_emb_code + ((size_t)q * p.num_audio + ldg_cg(&id[q])) * KC + k];
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            if (q < p.num_vq) {
+              const int id = sidx > 0 ? s_ids[b * 8 + q] : ldg_cg(p.ids_out + ((size_t)b * p.max_new + (ngen - 1)) * p.num_vq + q);
+              ev[it_][q] = p.W[p.o_emb_code + ((size_t)q * p.num_audio + id) * KC + k];
+            }
         }
       }
     }
-    xs[i] = v;
+#pragma unroll
+    for (int it_ = 0; it_ < BT * 3; ++it_) {
+      float v = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v += ev[it_][q];   // q order as Embed.forward: 0 + e0 + e1 + ...
+      xs[tid + it_ * FL_THREADS] = v;
+    }
   }
   __syncthreads();
-
-  const int R = p.R, myrep = g.cta % R;
-  const int o_row = g.cta + g.G * warp;  // this warp's O-proj row (valid iff fl_o_valid)
+  FL_TRACE();
 
   for (int l = 0; l < p.L; ++l) {
     const float* Wl = p.W + p.layer0 + (int64_t)l * p.layer_stride;
     unsigned long long* par = p.arena + (size_t)(l & 1) * FL_PARITY_WORDS;
     unsigned long long* parn = p.arena + (size_t)((l + 1) & 1) * FL_PARITY_WORDS;
-    unsigned long long* qkvw = par + (size_t)FL_RMAX * FL_REP_STRIDE;
+    unsigned long long* qkvw = par + (size_t)FL_RMAX * FL_REP_STRIDE;  // FL_A_Q / KN / VN at the start of the tail
     const unsigned long long* myr = par + (size_t)myrep * FL_REP_STRIDE;
     const uint32_t tagl = base + 8u * (uint32_t)l;
 
     // ============ A: QKV + RoPE + KV append ============
     {
       float4 nw[6];
-      fl_load_nw(Wl + p.o_ln1, nw, lane);
       FL_EV(0);
+      fl_nw_wait1();
       if (l > 0) fl_stage768<BT>(p, myr + FL_A_X, tagl + FT_X, xs, wd, fw);
+      else __syncthreads();
       FL_EV(1);
+      fl_load_nw_s(s_nw1, nw, lane);
       float x[BT][24];
       fl_load_x<BT>(xs, x, lane);
       // residual of this warp's O-proj row (raw x), kept for phase C
@@ -719,12 +1032,50 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_flow(const __grid_constant__ 
             M = cm;
           }
         }
+        // The splits of a (row, head) meet at the split-0 unit, which publishes the merged 64 outputs: the O-proj phase of
+        // all 148 CTAs then stages 768 words per row instead of every CTA reading (and merging) every partial.
+        const int ns_u = min(g.u_nchunk, g.S);
         if (tid < 64) {
-          const size_t pidx = FL_A_P + ((size_t)(b * FL_HEADS + h) * FL_SMAX + g.u_split) * FL_PW;
-          for (int r = 0; r < R; ++r) {
-            unsigned long long* d = par + (size_t)r * FL_REP_STRIDE + pidx;
-            ll_st(d + tid, O, tagl + FT_P);
-            if (tid == 0) { ll_st(d + 64, M, tagl + FT_P); ll_st(d + 65, L, tagl + FT_P); }
+          unsigned long long* P = par + FL_A_P + ((size_t)(b * FL_HEADS + h) * FL_SMAX) * FL_PW;  // replica 0 only
+          float v = 0.f;
+          if (ns_u > 1 && g.u_split > 0) {
+            ll_st(P + (size_t)g.u_split * FL_PW + tid, O, tagl + FT_P);
+            if (tid == 0) { ll_st(P + (size_t)g.u_split * FL_PW + 64, M, tagl + FT_P); ll_st(P + (size_t)g.u_split * FL_PW + 65, L, tagl + FT_P); }
+          } else {
+            // split 0 (or the only split): same expressions and order as k_step's merge (s = 0 .. ns-1)
+            float om[FL_SMAX], mm[FL_SMAX], lm[FL_SMAX];
+            om[0] = O; mm[0] = M; lm[0] = L;
+            if (ns_u > 1) {
+              wd.spins = 0;
+              while (true) {
+                bool ok = true;
+#pragma unroll
+                for (int sp = 1; sp < FL_SMAX; ++sp)
+                  if (sp < ns_u) {
+                    const unsigned long long w0 = ll_ld(P + (size_t)sp * FL_PW + tid);
+                    unsigned long long w1, w2;
+                    ll_ld2(P + (size_t)sp * FL_PW + 64, w1, w2);
+                    ok = ok && ll_tag(w0) == tagl + FT_P && ll_tag(w1) == tagl + FT_P && ll_tag(w2) == tagl + FT_P;
+                    om[sp] = ll_val(w0); mm[sp] = ll_val(w1); lm[sp] = ll_val(w2);
+                  }
+                if (__all_sync(0xffffffffu, ok)) break;
+                if (__any_sync(0xffffffffu, fl_giveup(wd, 0x400))) { wd.dead = 1; break; }
+              }
+            }
+            float GM = -INFINITY;
+#pragma unroll
+            for (int sp = 0; sp < FL_SMAX; ++sp)
+              if (sp < ns_u) GM = fmaxf(GM, mm[sp]);
+            float GL = 0.f, GO = 0.f;
+#pragma unroll
+            for (int sp = 0; sp < FL_SMAX; ++sp)
+              if (sp < ns_u) {
+                const float w = expf(mm[sp] - GM);
+                GL = fmaf(w, lm[sp], GL);
+                GO = fmaf(w, om[sp], GO);
+              }
+            v = GO / GL;
+            for (int r = 0; r < R; ++r) ll_st(par + (size_t)r * FL_REP_STRIDE + FL_A_AO + (size_t)b * KC + h * 64 + tid, v, tagl + FT_AO);
           }
         }
         if (pend_kv) fl_ring_release(p, fw);
@@ -732,67 +1083,10 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_flow(const __grid_constant__ 
       FL_TRACE();
       FL_EV(5);
 
-      // ============ C: merge the attention splits, O-proj + residual ============
+      // ============ C: O-proj + residual on the merged attention output ============
       __syncthreads();  // xs (raw x) is no longer read by any warp of this CTA
-#pragma unroll 1
-      for (int b = 0; b < BT; ++b) {
-        const bool live = b < p.B && s_active[b];  // uniform over the CTA
-        const int ns = live ? min((s_pos[b] + FL_CH) / FL_CH, g.S) : 0;
-        float ov[3][FL_SMAX];
-        if (live) {
-          const unsigned long long* P = myr + FL_A_P + (size_t)b * FL_HEADS * FL_SMAX * FL_PW;
-          wd.spins = 0;
-          while (true) {
-            bool ok = true;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-              const int c = tid + 256 * k, hh = c >> 6, dd = c & 63;
-#pragma unroll
-              for (int sp = 0; sp < FL_SMAX; ++sp)
-                if (sp < ns) {
-                  const unsigned long long w = ll_ld(P + (size_t)(hh * FL_SMAX + sp) * FL_PW + dd);
-                  ok = ok && (ll_tag(w) == tagl + FT_P);
-                  ov[k][sp] = ll_val(w);
-                }
-            }
-            for (int i = tid; i < p.Hq * ns * 2; i += FL_THREADS) {
-              const int hh = i / (2 * ns), rem = i % (2 * ns), sp = rem >> 1, which = rem & 1;
-              const unsigned long long w = ll_ld(P + (size_t)(hh * FL_SMAX + sp) * FL_PW + 64 + which);
-              ok = ok && (ll_tag(w) == tagl + FT_P);
-              s_ml[(hh * FL_SMAX + sp) * 2 + which] = ll_val(w);
-            }
-            if (__syncthreads_and(ok)) break;
-            if (__syncthreads_or(fl_giveup(wd, 0x400))) { wd.dead = 1; break; }
-          }
-          if (tid < p.Hq) {  // softmax weights of the splits, once per head (same expressions / order as k_step's merge)
-            const float* ml = s_ml + tid * FL_SMAX * 2;
-            float GM = -INFINITY;
-            for (int sp = 0; sp < ns; ++sp) GM = fmaxf(GM, ml[2 * sp]);
-            float GL = 0.f;
-            for (int sp = 0; sp < ns; ++sp) {
-              const float w = expf(ml[2 * sp] - GM);
-              GL = fmaf(w, ml[2 * sp + 1], GL);
-              s_w[tid * FL_SMAX + sp] = w;
-            }
-            s_gl[tid] = GL;
-          }
-          __syncthreads();
-        }
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          const int c = tid + 256 * k, hh = c >> 6;
-          float v = 0.f;
-          if (live) {
-            float GO = 0.f;
-#pragma unroll
-            for (int sp = 0; sp < FL_SMAX; ++sp)
-              if (sp < ns) GO = fmaf(s_w[hh * FL_SMAX + sp], ov[k][sp], GO);
-            v = GO / s_gl[hh];
-          }
-          xs[b * KC + c] = v;
-        }
-      }
-      __syncthreads();
+      fl_nw_fetch(s_nw1, l + 1 < p.L ? Wl + p.layer_stride + p.o_ln1 : p.W + p.o_final_norm);
+      fl_stage768<BT>(p, myr + FL_A_AO, tagl + FT_AO, xs, wd, fw, s_active);
       FL_EV(6);
       if (fl_o_valid(g)) {
         fl_load_x<BT>(xs, x, lane);
@@ -812,10 +1106,11 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_flow(const __grid_constant__ 
     // ============ D: gate/up + SiLU * mul ============
     {
       float4 nw[6];
-      fl_load_nw(Wl + p.o_ln2, nw, lane);
+      fl_nw_wait1();
       __syncthreads();  // every warp is done with xs (attention output)
       FL_CK(8);
       fl_stage768<BT>(p, myr + FL_A_XO, tagl + FT_XO, xs, wd, fw);
+      fl_load_nw_s(s_nw2, nw, lane);
       FL_EV(9);
       FL_CK(9);
       if (tid < FL_ROWS * BT) {  // residual of the down-phase output elements (raw x')
@@ -894,13 +1189,16 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_flow(const __grid_constant__ 
           if (b < p.B) {  // one poll loop per batch row keeps the 64-bit words of only one row live
             const unsigned long long* ap = myr + FL_A_ACT + (size_t)b * p.I + warp * kslice;
             unsigned long long w[12];
+            // 148 x 8 warps reading 3 KiB each is 3.5 MB through L2 per round: spin on the first two words of every lane
+            // and read the rest once they are in; every word is still validated by its own tag.  (Arrival counters
+            // bumped with red.add by the producers were tried instead of the sentinel words: no faster, 356 vs 352 us.)
             wd.spins = 0;
+            bool sentinel_ok = false;
             while (true) {
-              // spin on the first two words only (148 x 8 warps polling 3 KiB each is 3.5 MB of L2 reads per round);
-              // every word is still validated by its own tag once the sentinels have arrived
               ll_ld2(ap + lane * 4, w[0], w[1]);
-              if (__all_sync(0xffffffffu, ll_tag(w[0]) == tagl + FT_ACT && ll_tag(w[1]) == tagl + FT_ACT)) {
-                bool ok = true;
+              if (sentinel_ok || __all_sync(0xffffffffu, ll_tag(w[0]) == tagl + FT_ACT && ll_tag(w[1]) == tagl + FT_ACT)) {
+                sentinel_ok = true;
+                bool ok = ll_tag(w[0]) == tagl + FT_ACT && ll_tag(w[1]) == tagl + FT_ACT;
                 ll_ld2(ap + lane * 4 + 2, w[2], w[3]);
 #pragma unroll
                 for (int i = 1; i < 3; ++i) {
@@ -919,6 +1217,7 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_flow(const __grid_constant__ 
         }
       }
       FL_EV(11);
+      int e_tasks = 0;
       {
         // both down tasks (<= 6 row slices) together, one butterfly, refills after the partial sums are in shared memory
         const int nr0 = fl_d_rows(g, 0, 4), nr1 = fl_d_rows(g, 4, FL_ROWS);
@@ -948,11 +1247,11 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_flow(const __grid_constant__ 
         constexpr int LPV = 32 / (8 * BT);
         const int vi = lane / LPV, k = vi / BT, b = vi % BT;
         if ((lane % LPV) == 0 && k < FL_ROWS) s_red[k][warp][b] = acc[0];
-        fl_ring_release(p, fw);
-        if (nr1 > 0) fl_ring_release(p, fw);
+        e_tasks = nr1 > 0 ? 2 : 1;
       }
       FL_EV(12);
       __syncthreads();
+      if (l + 1 < p.L) fl_nw_fetch(s_nw2, Wl + p.layer_stride + p.o_ln2);
       if (tid < FL_ROWS * BT * 8) {  // K slices summed in the order 0..7 (deterministic); 8 threads share an element's replicas
         const int e = tid >> 3, b = e % BT, j = e / BT, row = g.cta + g.G * j;
         if (row < KC && b < p.B) {
@@ -964,6 +1263,7 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_flow(const __grid_constant__ 
             ll_st(parn + (size_t)r * FL_REP_STRIDE + FL_A_X + (size_t)b * KC + row, out, tagl + 8u + FT_X);
         }
       }
+      for (int k = 0; k < e_tasks; ++k) fl_ring_release(p, fw);  // refills only after the layer's output is on its way
       FL_TRACE();
       FL_EV(13);
     }
@@ -973,9 +1273,10 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_flow(const __grid_constant__ 
   if (p.sample) {
     const unsigned long long* myr = p.arena + (size_t)(p.L & 1) * FL_PARITY_WORDS + (size_t)myrep * FL_REP_STRIDE;
     float4 nw[6];
-    fl_load_nw(p.W + p.o_final_norm, nw, lane);
+    fl_nw_wait();
     __syncthreads();
     fl_stage768<BT>(p, myr + FL_A_X, base + 8u * (uint32_t)p.L + FT_X, xs, wd, fw);
+    fl_load_nw_s(s_nw1, nw, lane);
     float x[BT][24];
     fl_load_x<BT>(xs, x, lane);
     fl_norm<BT>(x, nw, p.eps);
@@ -989,6 +1290,7 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_flow(const __grid_constant__ 
         }
     }
     const int nrows = p.rows_per_item * p.V;
+    const uint32_t tagh = base + 8u * (uint32_t)p.L + FT_LOGITS;
     for (int j = 0; fl_h_valid(g, j); ++j) {
       const int t = g.gw + j * g.NW;
       const float* slot = fl_ring_wait(p, fw, wd);
@@ -999,24 +1301,119 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_flow(const __grid_constant__ 
       const int b = lane / LPB;
       if ((lane % LPB) == 0 && b < p.B) {
         const int r0 = 2 * t, q0 = r0 / p.V, c0 = r0 % p.V;
-        p.logits[((size_t)b * p.rows_per_item + q0) * p.V + c0] = a0[0];
-        if (r0 + 1 < nrows) {
-          const int q1 = (r0 + 1) / p.V, c1 = (r0 + 1) % p.V;
-          p.logits[((size_t)b * p.rows_per_item + q1) * p.V + c1] = a1[0];
+        const int q1 = (r0 + 1) / p.V, c1 = (r0 + 1) % p.V;
+        if (ink) {  // to the sampler CTA of the row through tagged words
+          ll_st(tailw + FL_A_LOGITS + (size_t)(b * p.rows_per_item + q0) * FL_VPAD + c0, a0[0], tagh);
+          if (r0 + 1 < nrows) ll_st(tailw + FL_A_LOGITS + (size_t)(b * p.rows_per_item + q1) * FL_VPAD + c1, a1[0], tagh);
+        } else {
+          p.logits[((size_t)b * p.rows_per_item + q0) * p.V + c0] = a0[0];
+          if (r0 + 1 < nrows) p.logits[((size_t)b * p.rows_per_item + q1) * p.V + c1] = a1[0];
         }
       }
       fl_ring_release(p, fw);
     }
   }
   FL_TRACE();
+  __syncthreads();
+  if (tid < p.B && s_active[tid]) s_pos[tid]++;   // positions advance once per step
+  __syncthreads();
+  const bool more = ink && sidx + 1 < p.nsteps;
+  if (more) FL_PREP_STEP();
+  if constexpr (INK) {
+    if (ink) {
+      // ============ sampling tail (gpt.py:487-508) on one CTA per (row, codebook) ============
+      const uint32_t tagi = base + 8u * (uint32_t)p.L + FT_IDX;
+      if (g.cta < nrows_s) {
+        const int row = g.cta, qi = row % p.rows_per_item;
+        const unsigned long long* lw = tailw + FL_A_LOGITS + (size_t)row * FL_VPAD;
+        unsigned long long w[4];
+        wd.spins = 0;
+        while (true) {
+          bool ok = true;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (tid + 256 * k < p.V) { w[k] = ll_ld(lw + tid + 256 * k); ok = ok && ll_tag(w[k]) == base + 8u * (uint32_t)p.L + FT_LOGITS; }
+          if (__all_sync(0xffffffffu, ok)) break;
+          if (__any_sync(0xffffffffu, fl_giveup(wd, 0x600))) { wd.dead = 1; break; }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (tid + 256 * k < p.V) s_samp.x[tid + 256 * k] = ll_val(w[k]);
+        __syncthreads();
+        const int id = fl_sample_row(p.samp, p.q_noise, s_samp, p.V, row, qi, nwin, lstep, (p.trace && row == 0) ? p.trace + 3100 : nullptr);
+        if (tid == 0) {
+          ll_st(tailw + FL_A_IDX + row, __int_as_float(id), tagi);
+          const bool pen = p.samp.penalty_on && row < p.samp.penalty_max_ids;
+          if (pen) {  // slide the repetition window
+            if (nwin < p.samp.past_window) s_samp.win[nwin] = id;
+            else { for (int k = 0; k + 1 < nwin; ++k) s_samp.win[k] = s_samp.win[k + 1]; if (nwin > 0) s_samp.win[nwin - 1] = id; }
+          }
+        }
+        if (p.samp.penalty_on && row < p.samp.penalty_max_ids && nwin < p.samp.past_window) nwin++;
+        __syncthreads();
+      }
+      FL_TRACE();
+      // ============ finish / write-back / counters (gpt.py:512-525,572-577) - every CTA keeps the loop state ============
+      if (tid < nrows_s) {
+        unsigned long long w;
+        wd.spins = 0;
+        while (true) {
+          w = ll_ld(tailw + FL_A_IDX + tid);
+          if (ll_tag(w) == tagi) break;
+          if (fl_giveup(wd, 0x601)) break;
+        }
+        s_ids[(tid / p.rows_per_item) * 8 + tid % p.rows_per_item] = __float_as_int(ll_val(w));
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int notall = 0;
+        for (int b = 0; b < p.B; ++b) {
+          bool eos = false;
+          for (int q = 0; q < p.rows_per_item; ++q) eos |= (s_ids[b * 8 + q] == p.samp.eos_token);
+          const int fin = s_fin[b] || eos;
+          s_fin[b] = fin;
+          if (!fin) { s_end[b]++; notall = 1; }
+          if (blockIdx.x == 0) {
+            int32_t* dst = p.ids_w + ((size_t)b * p.max_new + ngen) * p.num_vq;
+            for (int q = 0; q < p.num_vq; ++q) dst[q] = s_ids[b * 8 + q];
+            p.finish[b] = (uint8_t)fin;
+            p.end_idx[b] = s_end[b];
+          }
+        }
+        s_allfin = !notall;
+        if (blockIdx.x == 0) {
+          if (!notall) p.st->all_finished = 1;
+          p.st->n_gen = ngen + 1;
+          p.st->step = lstep + 1;
+        }
+      }
+      __syncthreads();
+      FL_TRACE();
+    }
+  }
+  ngen++; lstep++;
+  base += FL_EPOCH_STEP;                           // no word of this step can satisfy the next one
+  if (!more || s_allfin) {
+    if (more) {  // tasks of the step that will not run are in flight: wait for them before the CTA may exit
+      const int outst = fw.it.n - fw.n;
+      for (int k = 0; k < outst; ++k) {
+        const int n = fw.n + k;
+        wd.spins = 0;
+        while (!fl_try_wait(fw.bars + (n % FL_SLOTS) * 8, (uint32_t)(n / FL_SLOTS) & 1u))
+          if (__any_sync(0xffffffffu, fl_giveup(wd, 0x700))) { wd.dead = 1; break; }
+      }
+    }
+    break;
+  }
+  }  // step loop
   if (blockIdx.x == 0) {
-    // positions advance once per step; the tag base advances so that no word of this launch can satisfy the next
-    if (tid < p.B && s_active[tid]) p.seq_len[tid] = s_pos[tid] + 1;
-    if (tid == 0) *p.epoch = base + FL_EPOCH_STEP;
+    if (tid < p.B) p.seq_len[tid] = s_pos[tid];
+    if (tid == 0) *p.epoch = base;
   }
 #undef FL_TRACE
 #undef FL_EV
 #undef FL_CK
+#undef FL_PREP_STEP
 }
 
 }  // namespace ctb

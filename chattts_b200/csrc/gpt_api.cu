@@ -617,7 +617,10 @@ static int launch_step_flow_t(const FlowP& fp, cudaStream_t s) {
   return CTB_OK;
 }
 
-static int launch_step_flow(ctb_gpt* h, int col, bool sample, cudaStream_t s) {
+static bool flow_ink(const ctb_gpt* h);
+
+// nsteps > 0: multi-step decode with the sampling tail inside the kernel (requires flow_ink(h)); 0: one step, logits out
+static int launch_step_flow(ctb_gpt* h, int col, bool sample, cudaStream_t s, int nsteps = 0) {
   const ctb_gpt_config& c = h->cfg;
   const ctb_gpt_layout& L = h->lay;
   FlowP m{};
@@ -635,6 +638,8 @@ static int launch_step_flow(ctb_gpt* h, int col, bool sample, cudaStream_t s) {
   m.hidden_out = h->hiddens_out; m.hidden_stride = h->max_new * c.hidden_size;
   m.rows_per_item = h->infer_text ? 1 : c.num_vq; m.V = h->infer_text ? c.num_text_tokens : c.num_audio_tokens;
   m.arena = h->flow_arena; m.epoch = h->flow_epoch; m.R = h->flow_R; m.trace = h->trace;
+  m.ink = nsteps > 0 ? 1 : 0; m.nsteps = nsteps > 0 ? nsteps : 1; m.samp = h->sampler; m.q_noise = h->q_noise;
+  m.finish = h->finish; m.end_idx = h->end_idx; m.ids_w = h->ids_out;
   switch (bt_for(h->B)) {
     case 1: return launch_step_flow_t<1>(m, s);
     case 2: return launch_step_flow_t<2>(m, s);
@@ -643,6 +648,12 @@ static int launch_step_flow(ctb_gpt* h, int col, bool sample, cudaStream_t s) {
 }
 
 static bool use_flow(const ctb_gpt* h) { return h->flow_ok && !h->use_tc && h->B <= h->flow_max_batch; }
+// decode steps of audio generation at B <= 2 sample inside k_flow and run many steps per launch
+static bool flow_ink(const ctb_gpt* h) {
+  static const bool off = getenv("CTB_FLOW_NO_INK") != nullptr;
+  return !off && use_flow(h) && !h->infer_text && h->B <= 2 && h->cfg.num_audio_tokens <= FL_VPAD &&
+         h->B * h->cfg.num_vq <= FL_SROWS && h->cfg.num_vq <= 8;
+}
 
 // One loop iteration.  col >= 0: prefill column `col` of the prompt; col < 0: decode step.
 // sample: run heads + sampler + finalize (last prompt column and every decode step).
@@ -712,7 +723,7 @@ extern "C" int ctb_gpt_profile_kernel(ctb_gpt* h, int32_t kind, void* stream) {
     if (h->steps_enqueued >= h->max_new || h->T0 + h->steps_enqueued >= h->cfg.max_context)
       return set_err(CTB_ERR_STATE, "no room for another step (max_new / max_context reached)");
     h->steps_enqueued++;
-    if (use_flow(h)) return launch_step_flow(h, -1, true, s);
+    if (use_flow(h)) return launch_step_flow(h, -1, true, s, flow_ink(h) ? 1 : 0);
     if (!(h->mega_ok && h->B <= 8)) return set_err(CTB_ERR_STATE, "one-kernel step unavailable for this handle/batch");
     return launch_step_mega(h, -1, true, s);
   }
@@ -832,6 +843,12 @@ extern "C" int ctb_gpt_begin(ctb_gpt* h, int32_t B, int32_t T0, const float* emb
   CTB_CUDA(cudaMemsetAsync(h->finish, 0, h->bpad_max, s));
   CTB_CUDA(cudaMemsetAsync(h->end_idx, 0, sizeof(int) * h->bpad_max, s));
   CTB_CUDA(cudaMemsetAsync(h->counter, 0, sizeof(int) * h->cfg.max_batch * h->cfg.num_heads, s));
+  if (h->flow_ok) {
+    // the dataflow step numbers its launches from 1 within a generate() call: tag base and arrival counters restart
+    static const unsigned e0 = FL_EPOCH_STEP;
+    CTB_CUDA(cudaMemcpyAsync(h->flow_epoch, &e0, sizeof(e0), cudaMemcpyHostToDevice, s));
+    CTB_CUDA(cudaMemsetAsync(h->flow_arena, 0, FL_ARENA_WORDS * sizeof(unsigned long long), s));
+  }
   if (h->use_tc) {
     const size_t d = h->cfg.hidden_size, I = h->cfg.intermediate_size;
     float* z768[] = {h->x_hi, h->x_lo, h->attn_hi, h->attn_lo};
@@ -864,6 +881,13 @@ extern "C" int ctb_gpt_decode(ctb_gpt* h, int32_t n_steps, void* stream) {
   n_steps = std::min(n_steps, h->max_new - h->steps_enqueued);
   if (n_steps <= 0) return CTB_OK;
   h->steps_enqueued += n_steps;
+  if (flow_ink(h)) {
+    // the whole loop body (step, sampling tail, finish bookkeeping) is inside k_flow: many iterations per launch
+    const int per_launch = h->trace ? 1 : 64;
+    for (int done = 0; done < n_steps; done += per_launch)
+      if ((rc = launch_step_flow(h, -1, true, s, std::min(per_launch, n_steps - done)))) return rc;
+    return CTB_OK;
+  }
   if (h->use_graph && !h->graph_exec) {
     // capture on a private stream (the caller's may be the legacy default stream, which cannot
     // be captured); the instantiated graph is then launched on the caller's stream

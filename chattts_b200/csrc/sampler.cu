@@ -42,22 +42,6 @@ __device__ __forceinline__ float block_max_f(float v, float* s_red) {
   return t;
 }
 
-// Philox4x32-10 (counter-based) for the unseeded path (manual_seed=None has no parity target)
-__device__ __forceinline__ uint32_t mulhi32(uint32_t a, uint32_t b) { return __umulhi(a, b); }
-__device__ float philox_exp1(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2) {
-  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-  uint32_t x0 = c0, x1 = c1, x2 = c2, x3 = 0x9E3779B9u;
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint32_t h0 = mulhi32(0xD2511F53u, x0), l0 = 0xD2511F53u * x0;
-    const uint32_t h1 = mulhi32(0xCD9E8D57u, x2), l1 = 0xCD9E8D57u * x2;
-    x0 = h1 ^ x1 ^ k0; x1 = l1; x2 = h0 ^ x3 ^ k1; x3 = l0;
-    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-  }
-  const float u = ((x0 >> 8) + 1) * (1.0f / 16777216.0f);  // (0, 1]
-  return -logf(u);
-}
-
 }  // namespace
 
 __global__ void __launch_bounds__(SAMPLE_THREADS) k_sample(const SampleP p) {
