@@ -80,7 +80,7 @@ struct ctb_gpt {
   unsigned long long* trace;  // CTB_MEGA_TRACE=1: per-phase timestamps of the last step
   bool flow_ok;      // dataflow decode step (flow.cuh), B <= 4: default back end for those batches
   int flow_R;        // replicas of the broadcast exchange regions (CTB_FLOW_R)
-  int flow_max_batch; // batches that use it (CTB_FLOW_MAX_BATCH, default 2)
+  int flow_max_batch; // batches that use it (CTB_FLOW_MAX_BATCH, default 4)
   unsigned long long* flow_arena;
   unsigned* flow_epoch;
   int steps_enqueued;  // loop iterations enqueued since ctb_gpt_begin (host-side bound for ctb_gpt_decode)
@@ -285,9 +285,9 @@ extern "C" int ctb_gpt_create(const ctb_gpt_config* c, const float* weights_dev,
     const unsigned e0 = FL_EPOCH_STEP;
     cudaMemcpy(h->flow_epoch, &e0, sizeof(e0), cudaMemcpyHostToDevice);
     // measured on B200 (tools/flow_check.py): one copy of the exchange words is fastest (replicas multiply the 8-byte
-    // stores; the read hot-spot they were meant to relieve is the smaller effect), and the kernel wins up to B = 2
+    // stores; the read hot-spot they were meant to relieve is the smaller effect), and the kernel beats k_step at every batch it is built for (B <= 4)
     h->flow_R = getenv("CTB_FLOW_R") ? std::max(1, std::min(FL_RMAX, atoi(getenv("CTB_FLOW_R")))) : 1;
-    h->flow_max_batch = getenv("CTB_FLOW_MAX_BATCH") ? std::max(0, std::min(FL_BMAX, atoi(getenv("CTB_FLOW_MAX_BATCH")))) : 2;
+    h->flow_max_batch = getenv("CTB_FLOW_MAX_BATCH") ? std::max(0, std::min(FL_BMAX, atoi(getenv("CTB_FLOW_MAX_BATCH")))) : FL_BMAX;
   }
 #undef TRY
   // static page assignment: row b owns pages [b*ppr, (b+1)*ppr); kernels only see the table
