@@ -33,7 +33,8 @@ class SamplerConfig(C.Structure):
         ("temperature", C.c_float * 8), ("top_p", C.c_float), ("top_k", C.c_int32),
         ("min_tokens_to_keep", C.c_int32), ("penalty_on", C.c_int32), ("penalty_lut", C.c_float * 32),
         ("past_window", C.c_int32), ("penalty_max_ids", C.c_int32), ("greedy", C.c_int32),
-        ("eos_token", C.c_int32), ("min_new_token", C.c_int32), ("philox_seed", C.c_uint64)]
+        ("eos_token", C.c_int32), ("min_new_token", C.c_int32), ("top_p_removed_max", C.c_float),
+        ("has_removed_max", C.c_int32), ("philox_seed", C.c_uint64)]
 
 
 class GptStatus(C.Structure):
@@ -110,7 +111,7 @@ def load(build_if_missing: bool = True):
         lib.ctb_decoder_destroy.argtypes = [vp]
         lib.ctb_dvae_decode.argtypes = [vp, vp, i32, i32, i32, vp, vp]
         lib.ctb_vocos_decode.argtypes = [vp, vp, i32, i32, vp, vp]
-        if lib.ctb_abi_version() != 1:
+        if lib.ctb_abi_version() != 2:
             raise CtbError("ABI version mismatch")
         _lib = lib
         return lib

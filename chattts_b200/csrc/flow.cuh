@@ -314,6 +314,16 @@ __device__ __forceinline__ void fl_ring_wait_n(const FlowP& p, FlowW& w, int cnt
     if (__any_sync(0xffffffffu, fl_giveup(wd, 0x120))) { wd.dead = 1; break; }
   }
 }
+// non-blocking look at tasks n .. n + cnt - 1: issued before a phase polls its inputs so that the try_wait latency
+// (~200 cycles) overlaps the poll / RMSNorm; the blocking wait runs only if the tasks were not in yet
+__device__ __forceinline__ bool fl_ring_peek_n(const FlowP& p, FlowW& w, int cnt) {
+  fl_ensure(p, w, cnt);
+  bool ok = true;
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+    if (k < cnt) { const int n = w.n + k; ok = fl_try_wait(w.bars + (n % FL_SLOTS) * 8, (uint32_t)(n / FL_SLOTS) & 1u) && ok; }
+  return ok;
+}
 __device__ __forceinline__ const float* fl_ring_wait(const FlowP& p, FlowW& w, FlowWd& wd) {
   fl_ring_wait_n(p, w, 1, wd);
   return fl_ring_slot_at(w, 0);
@@ -588,7 +598,7 @@ __device__ __noinline__ int fl_sample_row(const ctb_sampler_config& c, const flo
     }
     FL_SK();
     const float denf = (float)den;
-    const float pthr = (float)(1.0 - (double)c.top_p);
+    const float pthr = c.has_removed_max ? c.top_p_removed_max : (float)(1.0 - (double)c.top_p);
     uint32_t key[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) { const int vt = tid + 256 * k; key[k] = vt < V ? float_key(sm.x[vt]) : 0u; }
@@ -853,6 +863,7 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_flow(const __grid_constant__ 
       float4 nw[6];
       FL_EV(0);
       fl_nw_wait1();
+      const bool q_rdy = fl_ring_peek_n(p, fw, 1);
       if (l > 0) fl_stage768<BT>(p, myr + FL_A_X, tagl + FT_X, xs, wd, fw);
       else __syncthreads();
       FL_EV(1);
@@ -867,7 +878,8 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_flow(const __grid_constant__ 
 #pragma unroll 1
       for (int j = 0; j < FL_QR; ++j) {
         if (!fl_q_valid(g, j)) continue;
-        const float* slot = fl_ring_wait(p, fw, wd);
+        if (!(j == 0 && q_rdy)) fl_ring_wait_n(p, fw, 1, wd);
+        const float* slot = fl_ring_slot_at(fw, 0);
         FL_EV(2);
         float a0[BT], a1[BT];
         fl_dot2<BT>(slot, x, a0, a1, lane);
@@ -905,32 +917,14 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_flow(const __grid_constant__ 
       if (g.u_on) {
         const int sub = lane & 7, grp = lane >> 3;
         const int b = g.u_b, h = g.u_h, n = g.u_n, pos = n - 1;
-        // q slice of this lane: dims sub*8 .. sub*8+7
-        float q[8];
-        {
-          const unsigned long long* qp = qkvw + FL_A_Q + b * KC + h * 64 + sub * 8;
-          unsigned long long w[8];
-          wd.spins = 0;
-          while (true) {
-            bool ok = true;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) ll_ld2(qp + 2 * k, w[2 * k], w[2 * k + 1]);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) ok = ok && (ll_tag(w[k]) == tagl + FT_QKV);
-            if (__all_sync(0xffffffffu, ok)) break;
-            if (__any_sync(0xffffffffu, fl_giveup(wd, 0x300))) { wd.dead = 1; break; }
-          }
-#pragma unroll
-          for (int k = 0; k < 8; ++k) q[k] = ll_val(w[k]);
-        }
-        FL_EV(4);
+        float q[8];  // q slice of this lane: dims sub*8 .. sub*8+7 (polled after the first chunk's K/V are in registers)
         float M = -INFINITY, L = 0.f, O = 0.f;
         int pend_kv = 0;
         for (int sb = 0;; ++sb) {
           int chunk;
           if (!fl_kv_more(g, sb, chunk)) break;
           const bool have = fl_kv_valid(g, chunk);
-          const float* slot = have ? fl_ring_wait(p, fw, wd) : nullptr;
+          const float* slot = have ? fl_ring_wait(p, fw, wd) : nullptr;  // usually complete long ago (prefetched a phase early)
           const int tbase = chunk * FL_CH + warp * 8 + grp;
           float4 k0[2], k1[2], v0[2], v1[2];
 #pragma unroll
@@ -944,6 +938,23 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_flow(const __grid_constant__ 
               v0[i] = *reinterpret_cast<const float4*>(vr); v1[i] = *reinterpret_cast<const float4*>(vr + 4);
             }
           }
+          if (sb == 0) {  // K/V of earlier tokens never depend on this step: they are loaded before q is waited for
+            const unsigned long long* qp = qkvw + FL_A_Q + b * KC + h * 64 + sub * 8;
+            unsigned long long w[8];
+            wd.spins = 0;
+            while (true) {
+              bool ok = true;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) ll_ld2(qp + 2 * k, w[2 * k], w[2 * k + 1]);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) ok = ok && (ll_tag(w[k]) == tagl + FT_QKV);
+              if (__all_sync(0xffffffffu, ok)) break;
+              if (__any_sync(0xffffffffu, fl_giveup(wd, 0x300))) { wd.dead = 1; break; }
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) q[k] = ll_val(w[k]);
+          }
+          if (sb == 0) FL_EV(4);
           // the token of THIS step: its K/V rows arrive from the QKV phase through the LL region, not the cache
           {
             const bool mine0 = (tbase == pos), mine1 = (tbase + 4 == pos);
@@ -1086,11 +1097,13 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_flow(const __grid_constant__ 
       // ============ C: O-proj + residual on the merged attention output ============
       __syncthreads();  // xs (raw x) is no longer read by any warp of this CTA
       fl_nw_fetch(s_nw1, l + 1 < p.L ? Wl + p.layer_stride + p.o_ln1 : p.W + p.o_final_norm);
+      const bool o_rdy = fl_o_valid(g) ? fl_ring_peek_n(p, fw, 1) : true;
       fl_stage768<BT>(p, myr + FL_A_AO, tagl + FT_AO, xs, wd, fw, s_active);
       FL_EV(6);
       if (fl_o_valid(g)) {
         fl_load_x<BT>(xs, x, lane);
-        const float* slot = fl_ring_wait(p, fw, wd);
+        if (!o_rdy) fl_ring_wait_n(p, fw, 1, wd);
+        const float* slot = fl_ring_slot_at(fw, 0);
         FL_EV(7);
         float a0[BT];
         fl_dot1<BT>(slot, x, a0, lane);
@@ -1107,6 +1120,10 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_flow(const __grid_constant__ 
     {
       float4 nw[6];
       fl_nw_wait1();
+      int ngu = 0;
+#pragma unroll
+      for (int j = 0; j < FL_GU; ++j) ngu += fl_gu_valid(g, j, p.I) ? 1 : 0;
+      const bool gu_rdy = fl_ring_peek_n(p, fw, ngu);
       __syncthreads();  // every warp is done with xs (attention output)
       FL_CK(8);
       fl_stage768<BT>(p, myr + FL_A_XO, tagl + FT_XO, xs, wd, fw);
@@ -1125,14 +1142,11 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_flow(const __grid_constant__ 
       {
         // all (<= 3) gate/up pair tasks of the warp at once: one pass over the activations, ONE butterfly for the six
         // row sums, the slot refills issued after the stores (they cost ~500 cycles each and nothing waits for them)
-        int ngu = 0;
-#pragma unroll
-        for (int j = 0; j < FL_GU; ++j) ngu += fl_gu_valid(g, j, p.I) ? 1 : 0;
         FL_CK(0);
         const float4* sl[FL_GU];
 #pragma unroll
         for (int j = 0; j < FL_GU; ++j) sl[j] = reinterpret_cast<const float4*>(fl_ring_slot_at(fw, j)) + lane;
-        fl_ring_wait_n(p, fw, ngu, wd);
+        if (!gu_rdy) fl_ring_wait_n(p, fw, ngu, wd);
         FL_CK(1);
         float acc[8 * BT];
 #pragma unroll
@@ -1180,6 +1194,8 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_flow(const __grid_constant__ 
     // ============ E: down + residual (K = 3072 split over the 8 warps) ============
     {
       float xd[BT][12];
+      const int nr0_ = fl_d_rows(g, 0, 4), nr1_ = fl_d_rows(g, 4, FL_ROWS);
+      const bool d_rdy = fl_ring_peek_n(p, fw, nr1_ > 0 ? 2 : 1);
       {
         const int kslice = p.I / FL_WARPS;  // 384
 #pragma unroll
@@ -1220,10 +1236,10 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_flow(const __grid_constant__ 
       int e_tasks = 0;
       {
         // both down tasks (<= 6 row slices) together, one butterfly, refills after the partial sums are in shared memory
-        const int nr0 = fl_d_rows(g, 0, 4), nr1 = fl_d_rows(g, 4, FL_ROWS);
+        const int nr0 = nr0_, nr1 = nr1_;
         const float* s0 = fl_ring_slot_at(fw, 0);
         const float* s1 = nr1 > 0 ? fl_ring_slot_at(fw, 1) : s0;
-        fl_ring_wait_n(p, fw, nr1 > 0 ? 2 : 1, wd);
+        if (!d_rdy) fl_ring_wait_n(p, fw, nr1 > 0 ? 2 : 1, wd);
         float acc[8 * BT];
 #pragma unroll
         for (int k = 0; k < 8 * BT; ++k) acc[k] = 0.f;

@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) k_sample(const SampleP p) {
       den = block_sum_d(den, s_redd);
     }
     const float denf = (float)den;
-    const float pthr = (float)(1.0 - (double)c.top_p);  // `cum <= (1 - top_p)` evaluated in fp32
+    const float pthr = c.has_removed_max ? c.top_p_removed_max : (float)(1.0 - (double)c.top_p);  // `cum <= (1 - top_p)` evaluated in fp32
     if (V <= 1024) {
       // ---------- sort path: bitonic sort of 1024 keys (pads = 0 sort first).  One key per thread in a register;
       // compare-exchange distances < 32 are warp shuffles, the 15 longer ones go through two alternating

@@ -259,8 +259,9 @@ class GPT:
             if attention_mask is None:
                 attention_mask = torch.ones(B, T0, dtype=torch.bool)
             mask_d = attention_mask.to(dev).to(torch.uint8).contiguous()
-            if not bool(mask_d[:, -1].all()):
-                raise ValueError("attention_mask must be left padded (last prompt column valid)")
+            # left padding (tokenizer.py:79-110): every row's valid tokens are a contiguous suffix ending in the last column
+            if not bool(mask_d[:, -1].all()) or (T0 > 1 and bool((mask_d[:, 1:] < mask_d[:, :-1]).any())):
+                raise ValueError("attention_mask must be left padded: each row 0...0 1...1 with the last column valid")
             q_d = None
             if seed is not None:
                 q_d = exp_noise(B * rows_per_item, V, seed).to(dev, non_blocking=True)

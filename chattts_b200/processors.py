@@ -106,6 +106,9 @@ def build_sampler_config(logits_processors: Sequence[object], temperature: Seque
             kind = 2
             cfg.top_p = float(proc.top_p)
             cfg.min_tokens_to_keep = int(getattr(proc, "min_tokens_to_keep", 1))
+            # HF: `cumulative_probs <= (1 - self.top_p)` - the python double 1 - top_p, cast to the fp32 of the tensor
+            cfg.top_p_removed_max = 1.0 - float(proc.top_p)
+            cfg.has_removed_max = 1
         elif hasattr(proc, "top_k"):
             kind = 3
             cfg.top_k = int(proc.top_k)  # HF already folded max(top_k, min_tokens_to_keep)

@@ -125,7 +125,7 @@ def synth_dvae_state(seed: int, stack: ConvStackConfig, dim: int, vq: VQConfig |
     return s
 
 
-def synth_vocos_state(seed: int = 5, cfg: VocosConfig = VocosConfig()) -> State:
+def synth_vocos_state(seed: int = 5, cfg: VocosConfig = VocosConfig(), mag_shift: float = -4.0) -> State:
     """Vocos backbone + ISTFT head keys ([3p] vocos; SURVEY.md §8b seam 2)."""
     g = _gen(seed)
     s: State = {}
@@ -138,7 +138,7 @@ def synth_vocos_state(seed: int = 5, cfg: VocosConfig = VocosConfig()) -> State:
     s["backbone.final_layer_norm.bias"] = _normal(g, (cfg.dim,), 0.05)
     _linear(g, s, "head.out", cfg.n_fft + 2, cfg.dim)
     # keep exp(mag) well below the clip at 100: shift the magnitude half
-    s["head.out.bias"][: cfg.n_fft // 2 + 1] -= 4.0
+    s["head.out.bias"][: cfg.n_fft // 2 + 1] += mag_shift
     s["head.istft.window"] = torch.hann_window(cfg.n_fft)
     return s
 

@@ -26,7 +26,7 @@ extern "C" {
 #define CTB_ERR_STATE (-3)
 #define CTB_ERR_NOMEM (-4)
 
-#define CTB_ABI_VERSION 1
+#define CTB_ABI_VERSION 2
 
 /* ---- library ------------------------------------------------------------------- */
 int ctb_abi_version(void);
@@ -94,6 +94,10 @@ typedef struct ctb_sampler_config {
                                2: arg-max over the non-EOS tokens (EOS removed as well) */
   int32_t eos_token;
   int32_t min_new_token;
+  float top_p_removed_max;  /* float32(1 - top_P) evaluated by the host exactly like HF TopPLogitsWarper (python double
+                               arithmetic, then the fp32 comparison `cum <= 1 - top_p`); used when has_removed_max != 0,
+                               otherwise the kernel derives it from the fp32 top_p (ABI v1 behaviour) */
+  int32_t has_removed_max;
   uint64_t philox_seed;     /* used only when q_noise == NULL (manual_seed=None path) */
 } ctb_sampler_config;
 
@@ -107,7 +111,8 @@ int ctb_gpt_destroy(ctb_gpt* h);
 /* Start one generate() call.  Replaces gpt.py:343-381 (buffer set-up) and the i == 0
  * iteration (prefill + first sample).
  *   emb_dev      [B, T0, d] fp32   prompt embeddings (Embed.forward output, embed.py:51-79)
- *   mask_dev     [B, T0]   uint8   attention_mask (left padded; any 0/1 pattern is honoured)
+ *   mask_dev     [B, T0]   uint8   attention_mask; every row's valid tokens must be a contiguous SUFFIX (left padding,
+ *                                  tokenizer.py:79-110) with the last column valid - the host mirror checks it
  *   q_noise_dev  [rows, V] fp32    Exp(1) noise of the seeded torch generator (gpt.py:504-508),
  *                                  rows = B*num_vq (audio) or B (text); NULL => device Philox
  *   ids_out_dev  [B, max_new, num_vq] int32   sampled ids (text: id replicated, gpt.py:521-523)

@@ -38,5 +38,5 @@ def test_layout_query_matches_parameter_count():
 
 
 def test_sampler_config_struct_size_matches_header():
-    # 8 floats + float + 3 ints + 1 int + 32 floats + 5 ints + pad + u64
-    assert ctypes.sizeof(_lib.SamplerConfig) == 8 * 4 + 4 + 4 + 4 + 4 + 32 * 4 + 4 * 5 + 4 + 8
+    # 8 floats + float + 3 ints + 1 int + 32 floats + 5 ints + float + int (ABI v2) + pad + u64
+    assert ctypes.sizeof(_lib.SamplerConfig) == 8 * 4 + 4 + 4 + 4 + 4 + 32 * 4 + 4 * 5 + 4 + 4 + 4 + 8

@@ -144,12 +144,14 @@ def test_streaming_yields_cumulative_chunks():
 
 
 @pytest.mark.parametrize("env,lengths", [({"CTB_GPT_TC": "1"}, [5, 12, 9]), ({"CTB_GPT_TC": "1"}, [16]),
-                                         ({"CTB_MEGA_MAX_BATCH": "8"}, [5, 12, 9]), ({"CTB_NO_MEGA": "1"}, [16]),
-                                         ({"CTB_NO_GRAPH": "1", "CTB_NO_PDL": "1"}, [7, 3])])
+                                         ({"CTB_NO_FLOW": "1", "CTB_MEGA_MAX_BATCH": "8"}, [5, 12, 9]),
+                                         ({"CTB_NO_FLOW": "1"}, [16]), ({"CTB_NO_FLOW": "1", "CTB_NO_MEGA": "1"}, [16]),
+                                         ({"CTB_NO_FLOW": "1", "CTB_NO_MEGA": "1", "CTB_NO_GRAPH": "1", "CTB_NO_PDL": "1"}, [7, 3]),
+                                         ({"CTB_FLOW_NO_INK": "1"}, [7, 3]), ({"CTB_FLOW_R": "4"}, [5, 12, 9, 3])])
 def test_every_decode_back_end_gives_the_same_ids(env, lengths):
-    """The three step implementations - PDL-chained FMA kernels, the one-kernel cooperative step (mega.cuh) and the
-    tcgen05 3xTF32 GEMM step (tc_decode.cuh) - are selected by batch size; each is forced here on batches it would
-    not get by default and must reproduce the CPU oracle's ids exactly."""
+    """The step implementations - the dataflow step (flow.cuh, default for B <= 4), the grid-barrier one-kernel step
+    (mega.cuh), the PDL-chained FMA kernels and the tcgen05 3xTF32 GEMM step (tc_decode.cuh) - are selected by batch
+    size; each is forced here on batches it would not get by default and must reproduce the CPU oracle's ids exactly."""
     import os
 
     from chattts_b200.config import Config
@@ -288,3 +290,78 @@ def test_embed_prompt_kernel_matches_reference_embed_semantics():
     ids[0, -2:] = torch.randint(0, 626, (2, 4))
     got = embed(ids, tmask)
     assert got.is_cuda and torch.equal(got.cpu(), orc.embed_prompt(ids, tmask))
+
+
+@pytest.mark.parametrize("B", [24, 32])
+def test_tensor_core_back_end_full_batches_vs_oracle(B):
+    """the tcgen05 decode back end at the batch sizes it is the default for (17..32, NPAD = 32)
+    against the CPU oracle itself: ragged 8..128-token prompts (batched prefill), top-p 0.7 / top-k 20 / penalty 1.05."""
+    from gpu_util import build_gpt
+
+    gpt, embed, gs, es = build_gpt(max_batch=32, max_context=256)
+    orc = GPTOracle(gs, es)
+    g = torch.Generator().manual_seed(100 + B)
+    lengths = torch.randint(8, 129, (B,), generator=g).tolist()
+    steps = 48
+    ids, mask, tmask = synth_prompt_batch(lengths, seed=50 + B)
+    ref = orc.generate(orc.embed_prompt(ids, tmask), ids, torch.tensor([0.3] * 4), 625, attention_mask=mask,
+                       max_new_token=steps, min_new_token=steps, sampler=SamplerParams(), return_hidden=True, manual_seed=77)
+    out = _run(gpt, embed, lengths, 50 + B, 77, steps)[-1]
+    for b in range(B):
+        assert torch.equal(out.ids[b].cpu(), ref.ids[b]), (B, b)
+        assert (out.hiddens[b].cpu() - ref.hiddens[b]).abs().max() < 1e-4
+
+
+@pytest.mark.parametrize("lengths,steps,greedy", [([16], 512, True), ([16], 1100, False), ([16, 9, 30, 5], 300, False)])
+def test_long_context_vs_oracle(lengths, steps, greedy):
+    """BASELINE configs[1] exactly (16-token prompt + 512 forced greedy tokens), a 1100-step B=1 run
+    (contexts > 768 keys: every attention split walks several chunks, many KV pages) and a 300-step B=4 run, ids
+    bit-equal to the CPU oracle."""
+    from gpu_util import build_gpt
+
+    gpt, embed, gs, es = build_gpt(max_batch=4, max_context=1280)
+    orc = GPTOracle(gs, es)
+    ids, mask, tmask = synth_prompt_batch(lengths, seed=61)
+    sp = SamplerParams(greedy=True, greedy_exclude_eos=True) if greedy else SamplerParams()
+    ref = orc.generate(orc.embed_prompt(ids, tmask), ids, torch.tensor([0.3] * 4), 625, attention_mask=mask,
+                       max_new_token=steps, min_new_token=steps, sampler=sp, return_hidden=True, manual_seed=1234)
+    out = _run(gpt, embed, lengths, 61, 1234, steps, extra=(ArgmaxOnly(exclude_eos=True),) if greedy else ())[-1]
+    for b in range(len(lengths)):
+        assert out.ids[b].shape[0] == steps
+        same = out.ids[b].cpu() == ref.ids[b]
+        first = int((~same.all(-1)).float().argmax()) if not bool(same.all()) else -1
+        assert first == -1, (b, first, out.ids[b][first].tolist(), ref.ids[b][first].tolist())
+        assert (out.hiddens[b].cpu() - ref.hiddens[b]).abs().max() < 2e-4
+
+
+def test_multi_step_launch_matches_single_step_launches():
+    """The dataflow step kernel runs up to 64 decode iterations per launch with the sampling tail inside (csrc/flow.cuh);
+    CTB_FLOW_NO_INK=1 launches one step at a time with k_sample / k_finalize outside.  Same ids, same early stop."""
+    import os
+
+    from chattts_b200.config import Config
+    from chattts_b200.embed import Embed
+    from chattts_b200.gpt import GPT
+    from chattts_b200.synth import synth_embed_state, synth_gpt_state
+
+    gs, es = synth_gpt_state(0), synth_embed_state(1)
+    outs = {}
+    for tag, env in (("ink", {}), ("ext", {"CTB_FLOW_NO_INK": "1"})):
+        os.environ.update(env)
+        try:
+            embed = Embed(768, 626, 21178, 4).load_state_dict(es).to("cuda")
+            gpt = GPT(Config().gpt, embed, device="cuda", device_gpt="cuda", max_batch=2, max_context=400)
+            gpt.load_state(gs)
+            ids, mask, tmask = synth_prompt_batch([16, 9], seed=3)
+            warp, proc = gen_logits(num_code=625, top_P=0.7, top_K=20, repetition_penalty=1.05)
+            outs[tag] = list(gpt.generate(embed(ids, tmask), ids, temperature=torch.tensor([1.5] * 4), eos_token=625,
+                                          attention_mask=mask, max_new_token=200, min_new_token=2,
+                                          logits_processors=(*proc, *warp), return_hidden=True, show_tqdm=False,
+                                          manual_seed=7))[-1]
+        finally:
+            for k in env:
+                os.environ.pop(k, None)
+    for b in range(2):
+        assert torch.equal(outs["ink"].ids[b], outs["ext"].ids[b])
+        assert torch.equal(outs["ink"].hiddens[b], outs["ext"].hiddens[b])
+    assert len(outs["ink"].ids[0]) < 200  # high temperature: this row stops at an EOS well before max_new_token
