@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """bench.py - speech-tokens/s of the GPT decode hot path (BASELINE.json metric), one JSON line.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference|torch-cuda]
+                    [--config c2|c3] [--path gpt|decoder]
 
 A "step" is one whole ``generate`` pass of the hot path over one batch: a 16-token prompt and
 ``--tokens`` (512) forced speech tokens per row, greedy + EOS excluded (BASELINE.json configs[1];
@@ -10,6 +11,11 @@ mask, Exp(1) noise already on the device; CUDA events on the launching stream). 
 metric through the public ``GPT.generate`` call with HOST buffers (pinned prompt embeddings +
 noise H2D, sampled ids D2H inside the timed region).  N > 1: one process per GPU (torchrun),
 utterances sharded, one NCCL broadcast of the packed weights at load, no step-loop collective.
+
+``--config c3``: BASELINE configs[2] (batch 32, prompts of 8..128 tokens, refine-text pass then code pass, top-p 0.7 /
+top-k 20 / penalty 1.05).  ``--path decoder``: hot path 2 at BASELINE configs[3] (DVAE decoder + Vocos + iSTFT of
+64 x 10 s), audio-samples/s with a tensor-core roofline against a TF32 peak measured in the same run.
+``--impl torch-cuda``: the reference's own stack (HF LlamaModel, torch SDPA, eager PyTorch) on the same B200.
 """
 from __future__ import annotations
 
@@ -31,6 +37,8 @@ PROMPT_LEN = 16
 # streamed weight elements per audio step (20 layers + 41 norms + 4 heads)
 W_ELEMS = 190_698_240
 KV_BYTES_PER_TOKEN_ROW = 20 * 2 * 768 * 4  # 122,880 B per row per context token (read), same per step (write)
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE single-step k_flow<1> launch (ncu --set full, round 2; see profiles/)
+TRAFFIC_K_FLOW_B1 = 771_000_000
 
 
 def algorithmic_bytes_per_step(B: int, T: float) -> float:
@@ -116,7 +124,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     B, tokens = args.batch, args.tokens
     es = synth_embed_state(1)
     embed = Embed(768, 626, 21178, 4).load_state_dict(es).to(dev)
-    gpt = GPT(cfg.gpt, embed, device=dev, device_gpt=dev, max_batch=max(B, 32), max_context=PROMPT_LEN + tokens + 16)
+    gpt = GPT(cfg.gpt, embed, device=dev, device_gpt=dev, max_batch=max(B, 32), max_context=PROMPT_LEN + tokens + 128)
     if world > 1:
         # one NCCL broadcast of the packed blob at load; only rank 0 builds it
         blob = broadcast_weights(gpt, synth_gpt_state(0) if rank == 0 else None, src=0)
@@ -202,22 +210,39 @@ def run_ours(args, rank: int, world: int, local_rank: int):
 
     t_avg = PROMPT_LEN + tokens / 2
     step_bytes = algorithmic_bytes_per_step(B, t_avg)
-    step_us = ms_per_step * 1e3 / (tokens + PROMPT_LEN - 1)
-    one_kernel = B == 1 and not os.environ.get("CTB_NO_MEGA")
+    step_us = ms_per_step * 1e3 / tokens  # `tokens` loop iterations per pass; the 16-token prompt is one batched prefill inside the first
+    one_kernel = B <= 4 and not os.environ.get("CTB_NO_FLOW")
     kern = {}
     if one_kernel:
-        # B = 1 runs the whole step as ONE persistent cooperative kernel (k_step: 101 grid-barrier phases)
-        step_resident()  # fresh state: the hook advances the context by one token per call
+        # B <= 4: the decode loop is the persistent dataflow kernel k_flow (csrc/flow.cuh): one launch = 16 decode
+        # iterations (20 layers + heads + sampling tail each).  Timed with CUDA events around single launches.
+        roof_new = tokens + 112
+        ids_big = torch.zeros(B, roof_new, 4, dtype=torch.int32, device=dev)
+        from chattts_b200.processors import build_sampler_config
+        scfg_roof = build_sampler_config(procs, [0.3] * 4, 625, roof_new)
+        gpt.enqueue_generate(emb_d, mask_d, scfg_roof, q_d, roof_new, False, ids_big, None, n_steps=tokens - 1)
+        _lib.check(lib.ctb_gpt_profile_kernel(gpt._handle, 8, stream_ptr))  # warm-up launch (16 steps)
         torch.cuda.synchronize()
-        us = time_kind(7, 16, 1)
-        kbytes = algorithmic_bytes_per_step(B, PROMPT_LEN + tokens + 10)
+        ctx0 = PROMPT_LEN + tokens + 16  # context at the first timed iteration
+        reps, per = 5, 16
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            _lib.check(lib.ctb_gpt_profile_kernel(gpt._handle, 8, stream_ptr))
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / reps  # us per launch
+        kbytes = sum(algorithmic_bytes_per_step(B, ctx0 + i) for i in range(reps * per)) / reps
         achieved = kbytes / (us * 1e-6) / 1e9
-        roofline = {"bound": "hbm", "kernel": "k_step<1> (one launch = the whole decode step: 20 layers + heads, 101 phases)",
+        roofline = {"bound": "hbm", "kernel": f"k_flow<{1 if B == 1 else 2 if B == 2 else 4}> (one launch = {per} decode iterations: "
+                                              "20 layers + heads + sampling tail each, no grid barriers)",
                     "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                    "traffic": 771580416, "peak_source": peak_src, "bytes_per_launch": int(kbytes),
-                    "us_per_launch": round(us, 2),
-                    "traffic_note": "dram__bytes_read+write of one k_step<1> launch at context 64 from ncu --set full "
-                                    "(profiles/r01_k_step_b1_full_raw.csv); algorithmic bytes at that context: 770.8 MB"}
+                    "traffic": TRAFFIC_K_FLOW_B1 * per if B == 1 else None, "peak_source": peak_src,
+                    "bytes_per_launch": int(kbytes), "us_per_launch": round(us, 2), "steps_per_launch": per,
+                    "us_per_step_in_kernel": round(us / per, 2), "context_tokens": [ctx0, ctx0 + reps * per],
+                    "traffic_note": "dram__bytes_read+write of one single-step k_flow<1> launch from ncu --set full "
+                                    "(profiles/r02_k_flow_b1_full_raw.csv), times the steps per launch; a constant from "
+                                    "that capture, not measured in this run"}
     else:
         for kind, name in ((3, "gateup"), (4, "down"), (0, "qkv"), (2, "oproj"), (1, "k_attn"), (5, "heads"), (6, "k_sample")):
             kern[name] = time_kind(kind, 20, 20 if kind < 5 else 1)
@@ -253,7 +278,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             torch.cuda.synchronize()
             ms2 = e0.elapsed_time(e1) / 2
             sb = algorithmic_bytes_per_step(bb, t_avg)
-            us2 = ms2 * 1e3 / (tokens + PROMPT_LEN - 1)
+            us2 = ms2 * 1e3 / tokens
             sweep[f"batch_{bb}"] = {"value": round(bb * tokens / (ms2 / 1e3), 1), "unit": "speech-tokens/s",
                                     "ms_per_step": round(ms2, 2), "rtf": round((ms2 / 1e3) / (bb * tokens * 512 / 24000.0), 6),
                                     "step_us": round(us2, 1), "hbm_frac": round(sb / (us2 * 1e-6) / 1e9 / peak, 4)}
@@ -311,6 +336,362 @@ def bench_decoder(dev, B: int = 64, T: int = 469):
     return {"workload": f"DVAE decoder + Vocos + iSTFT, batch {B} x {T} tokens (10 s each), hidden path, tcgen05 3xTF32 GEMMs",
             "ms": round(ms, 2), "audio_samples_per_s": round(wav.numel() / (ms / 1e3), 1),
             "rtf": round((ms / 1e3) / (wav.numel() / 24000.0), 7), "tflops_fp32_equiv": round(flops / (ms / 1e3) / 1e12, 1)}
+
+
+# ------------------------------------------------------------------ hot path 2 as its own benchmark line
+DEC_B, DEC_T = 64, 469                      # BASELINE configs[3]: 64 utterances of 10 s (469 tokens = 938 mel frames)
+DEC_FLOP_PER_FRAME = 78.7e6                 # hidden path, decoder 25.86 + vocos 13.50 + iDFT MMAC per frame
+DEC_ALGO_BYTES = 92.2e6 + 157.8e6 + 61.4e6  # hiddens in + fp32 weights + waveform out
+# dram__bytes_read + dram__bytes_write of one tokens_to_wav call at C4 from the ncu launch list of this round
+# (profiles/r02_decoder_c4_launches_summary.txt); a constant from that capture
+DEC_TRAFFIC_C4 = None
+
+
+def measured_tf32_peak(dev):
+    """cuBLAS TF32 GEMM throughput measured live (torch.matmul fp32 with allow_tf32), best of 5: the denominator of the
+    path-2 roofline (MEASURED_PEAKS.json carries bf16 only)."""
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        n = 8192
+        a = torch.randn(n, n, device=dev)
+        b = torch.randn(n, n, device=dev)
+        for _ in range(2):
+            a @ b
+        torch.cuda.synchronize()
+        best = None
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            a @ b
+            e1.record()
+            torch.cuda.synchronize()
+            t = e0.elapsed_time(e1)
+            best = t if best is None else min(best, t)
+        return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def decoder_cpu_sample(rows: int = 2):
+    """Oracle restatement of DVAE decoder + Vocos + iSTFT (oracle/dvae_oracle.py) on the host cores, `rows` utterances
+    of 10 s: the CPU baseline of hot path 2."""
+    from chattts_b200.config import Config
+    from chattts_b200.synth import synth_dvae_state, synth_vocos_state
+    from oracle import dvae_oracle as O
+
+    cfg = Config()
+    ds, vs = synth_dvae_state(2, cfg.decoder, cfg.decoder.idim), synth_vocos_state(5)
+    x = torch.randn(rows, 768, DEC_T, generator=torch.Generator().manual_seed(1))
+    cores = os.cpu_count() or 1
+    threads = min(cores, 32)
+    torch.set_num_threads(threads)
+    O.vocos_decode(O.dvae_decode(x[:1], ds), vs)  # warm-up
+    t = time.perf_counter()
+    wav = O.vocos_decode(O.dvae_decode(x, ds), vs)
+    dt = time.perf_counter() - t
+    return {"value": round(wav.numel() / dt, 1), "unit": "audio-samples/s", "cores": threads, "kind": "port",
+            "sample": f"oracle/dvae_oracle.py dvae_decode + vocos_decode: {rows} utterances x {DEC_T} tokens (10 s each), "
+                      f"{threads} torch threads of a {cores}-core host ({dt:.2f} s)"}, dt
+
+
+def run_decoder(args, rank: int, world: int, local_rank: int):
+    """`--path decoder`: audio-samples/s of DVAE decoder + Vocos + iSTFT at BASELINE configs[3], per GPU 64 x 10 s."""
+    import torch.distributed as dist
+
+    from chattts_b200 import _lib
+    from chattts_b200.config import Config
+    from chattts_b200.decoder import DVAE, Vocos
+    from chattts_b200.synth import synth_dvae_state, synth_vocos_state
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    lib = _lib.load()
+    cfg = Config()
+    voc = Vocos(cfg.vocos, dev, max_batch=DEC_B, max_tokens=DEC_T)
+    voc.state = synth_vocos_state(5)
+    dec = DVAE(cfg.decoder, dim=cfg.decoder.idim, device=dev, vocos=voc, max_batch=DEC_B, max_tokens=DEC_T)
+    dec.load_state_dict(synth_dvae_state(2, cfg.decoder, cfg.decoder.idim))
+    x_host = torch.randn(DEC_B, DEC_T, 768, generator=torch.Generator().manual_seed(1 + rank)).pin_memory()
+    x_dev = x_host.to(dev)
+    wav_host = torch.empty(DEC_B, 512 * DEC_T - 256, dtype=torch.float32).pin_memory()
+
+    def step_resident():
+        return dec.engine.tokens_to_wav(x_dev, 1)
+
+    def step_e2e():
+        w = dec.engine.tokens_to_wav(x_host.to(dev, non_blocking=True), 1)
+        wav_host.copy_(w, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        barrier()
+        return ms
+
+    for _ in range(args.warmup):
+        step_resident()
+    l0 = lib.ctb_launch_count()
+    with ClockSampler(local_rank) as clk:
+        ms = timed(step_resident, args.steps) / args.steps
+    launches = int(lib.ctb_launch_count() - l0)
+    samples = DEC_B * (512 * DEC_T - 256)
+    value = world * samples / (ms / 1e3)
+    step_e2e()
+    ms_e2e = timed(step_e2e, max(1, min(args.steps, 5))) / max(1, min(args.steps, 5))
+    if rank != 0:
+        return None
+    tf32_peak = measured_tf32_peak(dev)
+    hbm_peak, hbm_src = measured_peaks()
+    flops = DEC_B * 2 * DEC_T * DEC_FLOP_PER_FRAME
+    ach = flops / (ms / 1e3) / 1e12
+    fma_ms = None
+    if not args.no_sweep:  # the fp32-FMA twin of the GEMMs (CTB_DECODER_FMA=1): what "no tensor cores on the conv path" costs
+        os.environ["CTB_DECODER_FMA"] = "1"
+        try:
+            voc2 = Vocos(cfg.vocos, dev, max_batch=DEC_B, max_tokens=DEC_T)
+            voc2.state = voc.state
+            dec2 = DVAE(cfg.decoder, dim=cfg.decoder.idim, device=dev, vocos=voc2, max_batch=DEC_B, max_tokens=DEC_T)
+            dec2.load_state_dict(synth_dvae_state(2, cfg.decoder, cfg.decoder.idim))
+            dec2.engine.tokens_to_wav(x_dev, 1)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            dec2.engine.tokens_to_wav(x_dev, 1)
+            e1.record()
+            torch.cuda.synchronize()
+            fma_ms = e0.elapsed_time(e1)
+        finally:
+            del os.environ["CTB_DECODER_FMA"]
+    cpu, _ = decoder_cpu_sample() if world == 1 else (None, None)
+    return {
+        "metric": "audio-samples/sec (DVAE decoder + Vocos + iSTFT, hidden-state path, 24 kHz)",
+        "value": round(value, 1), "unit": "audio-samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic (seeded random-init weights of the ChatTTS decoder / Vocos shapes, N(0,1) hidden states)",
+        "config": {"workload": f"hot path 2 at BASELINE configs[3]: batch {DEC_B}/GPU x {DEC_T} tokens (10 s each), GPT hidden "
+                               "states -> mel -> waveform; one step = one whole batch", "batch_per_gpu": DEC_B, "tokens": DEC_T,
+                   "parallelism": f"dp{world}",
+                   "l2_policy": "inputs larger than L2: 92 MB of hidden states in, 61 MB of waveform out and ~2 GB of "
+                                "intermediate activations per step (> 126 MB L2)"},
+        "rtf": round((ms / 1e3) / (world * samples / 24000.0), 8),
+        "e2e": {"value": round(world * samples / (ms_e2e / 1e3), 1), "unit": "audio-samples/s",
+                "h2d_bytes_per_step": int(x_host.numel() * 4), "d2h_bytes_per_step": int(wav_host.numel() * 4),
+                "ms_per_step": round(ms_e2e, 3)},
+        "gpu_launches": launches, "clocks": clk.summary(),
+        "roofline": {"bound": "tensor", "kernel": "k_tc_gemm<EPI> (tcgen05 3xTF32 conv-as-GEMM; 46 of the call's launches, >90 % of its time)",
+                     "achieved": round(ach, 1), "peak": round(tf32_peak, 1), "unit": "TFLOP/s", "frac": round(ach / tf32_peak, 4),
+                     "traffic": DEC_TRAFFIC_C4,
+                     "peak_source": "measured in this run: torch.matmul fp32 8192^3 with allow_tf32 (cuBLAS TF32), best of 5",
+                     "note": "achieved = ALGORITHMIC fp32 flops (4.73 TFLOP at C4) / step time; the 3xTF32 split issues 3 tensor MACs "
+                             "per algorithmic MAC, so the tensor pipes do 3x this figure",
+                     "tensor_work_frac": round(3 * ach / tf32_peak, 4),
+                     "hbm": {"algorithmic_bytes": int(DEC_ALGO_BYTES), "achieved_gbs": round(DEC_ALGO_BYTES / (ms / 1e3) / 1e9, 1),
+                             "peak_gbs": hbm_peak, "peak_source": hbm_src},
+                     "fma_twin_ms": None if fma_ms is None else round(fma_ms, 2)},
+        "cpu_baseline": cpu,
+    }
+
+
+def run_reference_decoder(args, rank: int):
+    if rank != 0:
+        return None
+    cpu, _ = decoder_cpu_sample()  # warm
+    vals = []
+    for _ in range(max(1, args.steps)):
+        c, dt = decoder_cpu_sample()
+        vals.append((c, dt))
+    c, dt = sorted(vals, key=lambda t: t[1])[len(vals) // 2]
+    return {"impl": "reference", "metric": "audio-samples/sec (DVAE decoder + Vocos + iSTFT, hidden-state path, 24 kHz)",
+            "value": c["value"], "unit": "audio-samples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(dt * 1e3, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": "hot path 2 at BASELINE configs[3]; reference arm times 2 of the 64 utterances"},
+            "cpu_baseline": c, "e2e": {"value": c["value"], "unit": "audio-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+# ------------------------------------------------------------------ the reference's own stack on the same GPU
+def run_torch_cuda(args, rank: int):
+    """`--impl torch-cuda` (BASELINE configs[1] "KV-cache kernel vs torch.sdpa"): HF LlamaModel in fp32 with SDPA attention and
+    its DynamicCache on the same B200, heads / temperature / penalty / greedy arg-max as eager torch ops - the reference's
+    library path (gpt.py:394-596) without its Python generator overhead.  Same synthetic weights, prompt and token count."""
+    if rank != 0:
+        return None
+    import dataclasses
+
+    from transformers import LlamaConfig, LlamaModel
+
+    from chattts_b200.config import Config
+    from chattts_b200.embed import Embed
+    from chattts_b200.prompts import synth_prompt_batch
+    from chattts_b200.synth import synth_embed_state, synth_gpt_state
+
+    dev = torch.device("cuda", 0)
+    c = Config().gpt
+    lc = LlamaConfig(hidden_size=c.hidden_size, intermediate_size=c.intermediate_size, num_attention_heads=c.num_attention_heads,
+                     num_key_value_heads=c.num_key_value_heads, num_hidden_layers=c.num_hidden_layers,
+                     max_position_embeddings=c.max_position_embeddings, rms_norm_eps=c.rms_norm_eps, vocab_size=32,
+                     attn_implementation="sdpa")
+    model = LlamaModel(lc).eval()
+    model.load_state_dict(synth_gpt_state(0), strict=False)
+    model = model.to(dev).float()
+    es = synth_embed_state(1)
+    embed = Embed(768, 626, 21178, 4).load_state_dict(es)
+    heads = torch.stack([embed.folded_head(f"head_code.{q}") for q in range(4)]).to(dev)        # [4, 626, 768]
+    emb_code = torch.stack([es[f"emb_code.{q}.weight"] for q in range(4)]).to(dev)              # [4, 626, 768]
+    B, tokens = args.batch, args.tokens
+    ids, mask, tmask = synth_prompt_batch([PROMPT_LEN] * B, seed=1)
+    emb0 = embed.to(dev)(ids, tmask).to(dev).float() if hasattr(embed, "to") else None
+    penalty = torch.pow(torch.tensor(1.05), torch.arange(17)).to(dev)
+
+    @torch.no_grad()
+    def gen(n):
+        out = model(inputs_embeds=emb0, use_cache=True)
+        past, h = out.past_key_values, out.last_hidden_state[:, -1]
+        hist = torch.zeros(B, 4, 0, dtype=torch.long, device=dev)
+        for i in range(n):
+            logits = torch.einsum("bd,qvd->bqv", h, heads) / 0.3
+            if hist.shape[2]:
+                cnt = torch.nn.functional.one_hot(hist[:, :, -16:], 626).sum(2)
+                a = penalty[cnt]
+                logits = torch.where(logits < 0, logits * a, logits / a)
+            logits[:, :, 625] = -float("inf")
+            idx = logits.argmax(-1)                                   # [B, 4]
+            hist = torch.cat([hist, idx[:, :, None]], 2)
+            x = emb_code[torch.arange(4, device=dev)[None], idx].sum(1, keepdim=True)   # [B, 1, 768]
+            out = model(inputs_embeds=x, past_key_values=past, use_cache=True)
+            past, h = out.past_key_values, out.last_hidden_state[:, -1]
+        return hist
+
+    n = tokens
+    for _ in range(max(1, min(args.warmup, 2))):
+        gen(min(n, 32))
+    torch.cuda.synchronize()
+    steps = max(1, min(args.steps, 3))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        gen(n)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    value = B * n / (ms / 1e3)
+    return {"impl": "torch-cuda", "metric": "speech-tokens/sec (GPT decode loop, 4-codebook tokens; RTF = wall / audio seconds @ 24 kHz)",
+            "value": round(value, 2), "unit": "speech-tokens/s", "n_gpus": 1, "steps": steps, "warmup": args.warmup,
+            "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic (same seeded weights / prompt as the other arms)",
+            "config": {"workload": f"HF LlamaModel fp32 + SDPA + DynamicCache, eager PyTorch on the same GPU: batch {B} x (16-token prompt + "
+                                   f"{n} greedy speech tokens)", "batch_per_gpu": B, "tokens": n, "prompt_len": PROMPT_LEN},
+            "us_per_token_step": round(ms * 1e3 / n, 1), "rtf": round((ms / 1e3) / (B * n * 512 / 24000.0), 6)}
+
+
+# ------------------------------------------------------------------ BASELINE configs[2]
+def run_c3(args, rank: int, world: int, local_rank: int):
+    """`--config c3`: batch 32 per GPU, prompt lengths U{8..128} (left padded), refine-text pass (infer_text, temperature 0.7,
+    top-p 0.7 / top-k 20, no penalty) then code pass (temperature 0.3, top-p 0.7 / top-k 20 / penalty 1.05, seed 42) through
+    the public GPT.generate API with host prompts.  Random weights have no meaningful EOS, so both passes run a FORCED
+    length (text 128, code `--tokens`); the metric is speech tokens of the code pass over the time of both passes."""
+    import torch.distributed as dist
+
+    from chattts_b200 import _lib
+    from chattts_b200.config import Config
+    from chattts_b200.dist import broadcast_weights
+    from chattts_b200.embed import Embed
+    from chattts_b200.gpt import GPT
+    from chattts_b200.processors import gen_logits
+    from chattts_b200.prompts import synth_prompt_batch
+    from chattts_b200.synth import synth_embed_state, synth_gpt_state
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    lib = _lib.load()
+    B, tokens, text_tokens = args.batch if args.batch > 1 else 32, args.tokens, 128
+    es = synth_embed_state(1)
+    embed = Embed(768, 626, 21178, 4).load_state_dict(es).to(dev)
+    gpt = GPT(Config().gpt, embed, device=dev, device_gpt=dev, max_batch=B, max_context=128 + max(tokens, text_tokens) + 16)
+    if world > 1:
+        gpt.load_state(None, weights_blob=broadcast_weights(gpt, synth_gpt_state(0) if rank == 0 else None, src=0))
+    else:
+        gpt.load_state(synth_gpt_state(0))
+    g = torch.Generator().manual_seed(7 + rank)
+    lengths = torch.randint(8, 129, (B,), generator=g).tolist()
+    ids, mask, tmask = synth_prompt_batch(lengths, seed=1 + rank)
+    warp_t, proc_t = gen_logits(num_code=21178, top_P=0.7, top_K=20, repetition_penalty=1.0)
+    warp_c, proc_c = gen_logits(num_code=625, top_P=0.7, top_K=20, repetition_penalty=1.05)
+
+    def pipeline():
+        emb = embed(ids, tmask)
+        list(gpt.generate(emb, ids, temperature=torch.tensor([0.7]), eos_token=21001, attention_mask=mask,
+                          max_new_token=text_tokens, min_new_token=text_tokens, logits_processors=(*proc_t, *warp_t),
+                          infer_text=True, show_tqdm=False, manual_seed=42))
+        out = list(gpt.generate(emb, ids, temperature=torch.tensor([0.3] * 4), eos_token=625, attention_mask=mask,
+                                max_new_token=tokens, min_new_token=tokens, logits_processors=(*proc_c, *warp_c),
+                                return_hidden=False, show_tqdm=False, manual_seed=42))[-1]
+        return [t.cpu() for t in out.ids]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        pipeline()
+    barrier()
+    steps = max(1, min(args.steps, 3))
+    l0 = lib.ctb_launch_count()
+    with ClockSampler(local_rank) as clk:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            pipeline()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    launches = int(lib.ctb_launch_count() - l0) // steps
+    if rank != 0:
+        return None
+    value = world * B * tokens / (ms / 1e3)
+    peak, peak_src = measured_peaks()
+    code_bytes = algorithmic_bytes_per_step(B, sum(lengths) / B + tokens / 2) * tokens
+    text_bytes = (algorithmic_bytes_per_step(B, sum(lengths) / B + text_tokens / 2) + 21178 * 768 * 4 - 4 * 626 * 768 * 4) * text_tokens
+    return {
+        "metric": "speech-tokens/sec (GPT decode loop, 4-codebook tokens; RTF = wall / audio seconds @ 24 kHz)",
+        "value": round(value, 2), "unit": "speech-tokens/s", "n_gpus": world, "steps": steps, "warmup": args.warmup,
+        "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic (seeded random-init weights of the ChatTTS GPT shape)",
+        "config": {"workload": f"BASELINE configs[2]: batch {B}/GPU, prompts of 8..128 tokens (left padded), refine-text pass "
+                               f"({text_tokens} forced text tokens) then code pass ({tokens} forced speech tokens), top-p 0.7 / top-k 20 / "
+                               "penalty 1.05, through GPT.generate with host prompts (value IS the end-to-end number)",
+                   "batch_per_gpu": B, "tokens": tokens, "text_tokens": text_tokens, "prompt_len": "8..128", "parallelism": f"dp{world}",
+                   "l2_policy": "inputs larger than L2: every decode iteration streams >= 763 MB of fp32 weights"},
+        "rtf": round((ms / 1e3) / (world * B * tokens * 512 / 24000.0), 6),
+        "e2e": {"value": round(value, 2), "unit": "speech-tokens/s", "h2d_bytes_per_step": int(ids.numel() * 8 + mask.numel()),
+                "d2h_bytes_per_step": int(B * tokens * 16), "ms_per_step": round(ms, 3)},
+        "gpu_launches": launches, "clocks": clk.summary(),
+        "roofline": {"bound": "hbm", "kernel": "whole pipeline (tcgen05 decode back end at B = 32, both passes)", "achieved":
+                     round((code_bytes + text_bytes) / (ms / 1e3) / 1e9, 1), "peak": peak, "unit": "GB/s",
+                     "frac": round((code_bytes + text_bytes) / (ms / 1e3) / 1e9 / peak, 4), "traffic": None, "peak_source": peak_src},
+        "cpu_baseline": None,
+    }
 
 
 def best_cpu_threads(run4, candidates=(16, 32, 64, 128)):
@@ -417,7 +798,9 @@ def main():
     ap.add_argument("--batch", type=int, default=int(os.environ.get("CTB_BENCH_BATCH", "1")))
     ap.add_argument("--tokens", type=int, default=512)
     ap.add_argument("--ref-tokens", type=int, default=48)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch-cuda"])
+    ap.add_argument("--config", default="c2", choices=["c2", "c3"], help="c2: BASELINE configs[1] (default); c3: configs[2]")
+    ap.add_argument("--path", default="gpt", choices=["gpt", "decoder"], help="decoder: hot path 2 at BASELINE configs[3]")
     ap.add_argument("--no-sweep", action="store_true", help="skip the short batch-8/32 and decoder side measurements")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
@@ -426,7 +809,12 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        line = run_reference(args, rank)
+        line = run_reference_decoder(args, rank) if args.path == "decoder" else run_reference(args, rank)
+        if line is not None:
+            print(json.dumps(line), flush=True)
+        return
+    if args.impl == "torch-cuda":
+        line = run_torch_cuda(args, rank)
         if line is not None:
             print(json.dumps(line), flush=True)
         return
@@ -436,7 +824,12 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
-        line = run_ours(args, rank, world, local_rank)
+        if args.path == "decoder":
+            line = run_decoder(args, rank, world, local_rank)
+        elif args.config == "c3":
+            line = run_c3(args, rank, world, local_rank)
+        else:
+            line = run_ours(args, rank, world, local_rank)
         if line is not None:
             print(json.dumps(line), flush=True)
     finally:

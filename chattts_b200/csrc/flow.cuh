@@ -26,6 +26,7 @@
 namespace ctb {
 
 constexpr int FL_THREADS = 256;
+constexpr int FL_LAUNCH_THREADS = FL_THREADS;
 constexpr int FL_WARPS = 8;
 constexpr int FL_SLOTS = 4;
 constexpr int FL_SLOT_BYTES = 6144;
@@ -62,6 +63,9 @@ constexpr unsigned FL_EPOCH_STEP = 256;  // tags of one launch: base + 8 * layer
 
 enum FlowTagKind { FT_X = 0, FT_QKV = 1, FT_P = 2, FT_XO = 3, FT_ACT = 4, FT_LOGITS = 5, FT_IDX = 6, FT_AO = 7 };
 enum FlowStage { FS_Q0 = 0, FS_Q1 = 1, FS_KV = 2, FS_O = 3, FS_GU0 = 4, FS_GU1 = 5, FS_GU2 = 6, FS_D0 = 7, FS_D1 = 8, FS_NLAYER = 9 };
+
+// barrier among the 8 consumer warps only (the loader warp never joins it)
+__device__ __forceinline__ void fl_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 struct FlowP {
   const float* W;  // packed fp32 blob
@@ -234,8 +238,8 @@ __device__ __noinline__ int fl_build_table(const FlowP& p, const FlowGeo* gs, in
 }
 
 // heads tasks (after the last layer): rare, computed directly
-__device__ __noinline__ void fl_issue_heads(const FlowP& p, const FlowGeo* gs, int hsub, uint32_t dst, uint32_t bar, uint64_t pol_w) {
-  const int gw = gs->cta * FL_WARPS + (threadIdx.x >> 5);
+__device__ __forceinline__ void fl_issue_heads(const FlowP& p, const FlowGeo* gs, int w, int hsub, uint32_t dst, uint32_t bar, uint64_t pol_w) {
+  const int gw = gs->cta * FL_WARPS + w;
   const int t = gw + hsub * gs->NW, nrows = p.rows_per_item * p.V;
   if (fl_elect()) {
     fl_expect(bar, 2u * KC * 4u);
@@ -244,8 +248,9 @@ __device__ __noinline__ void fl_issue_heads(const FlowP& p, const FlowGeo* gs, i
   }
 }
 
-// Post the bulk copies of the next task into slot it.n % FL_SLOTS (lane 0) and advance the iterator.
-__device__ __forceinline__ void fl_issue(const FlowP& p, const FlowGeo* gs, const int4* tab, FlowIss& it, uint32_t ring,
+// Post the bulk copies of consumer warp w's next task into slot it.n % FL_SLOTS (one elected lane) and advance the
+// iterator.  Returns false at the end of the step's sequence.
+__device__ __forceinline__ bool fl_issue(const FlowP& p, const FlowGeo* gs, const int4* tab, FlowIss& it, int w, uint32_t ring,
                                          uint32_t bars, uint64_t pol_w, uint64_t pol_kv) {
   const int slot = it.n % FL_SLOTS;
   const uint32_t bar = bars + slot * 8, dst = ring + slot * FL_SLOT_BYTES;
@@ -261,17 +266,23 @@ __device__ __forceinline__ void fl_issue(const FlowP& p, const FlowGeo* gs, cons
     }
     if (++it.k == it.ntab) { it.k = 0; it.l++; }
     it.n++;
-  } else if (gs->cta * FL_WARPS + (int)(threadIdx.x >> 5) + it.hsub * gs->NW < gs->nheads_tasks) {
-    fl_issue_heads(p, gs, it.hsub, dst, bar, pol_w);
+    return true;
+  }
+  if (gs->cta * FL_WARPS + w + it.hsub * gs->NW < gs->nheads_tasks) {
+    fl_issue_heads(p, gs, w, it.hsub, dst, bar, pol_w);
     it.hsub++;
     it.n++;
+    return true;
   }
+  return false;
 }
 
-// Per-warp ring state.  Consumed slots are NOT refilled on the spot: posting the bulk copies of the next task costs
-// ~500 cycles (expect_tx + UBLKCP issue), which used to sit between a task's stores and the next poll.  The warp
-// only counts what it owes (`owed`) and pays while it is waiting anyway: every failed poll iteration posts one refill;
-// a wait on the ring first posts whatever the tasks it is about to consume need.
+// Per-warp ring state.  The consuming warp refills a slot itself, right after the stores of the phase that emptied it.
+// Two alternatives were built and measured on B200 (tools/flow_check.py, B = 1, 256 tokens):
+//   * lazy refills inside the poll loops (one per failed poll): 20-40 % slower (longer poll period);
+//   * a loader warpgroup (4 warps posting every copy of the CTA, consumers only publish a counter, registers moved
+//     with setmaxnreg): 360-380 us/step against 323 - the X edge grew from ~0.8 to ~2.5 us while the copies were posted
+//     concurrently with the polls.
 struct FlowW {
   float* base;      // this warp's slots (generic pointer)
   uint32_t ring;    // same, shared-space address
@@ -286,18 +297,24 @@ struct FlowW {
 __device__ __forceinline__ void fl_refill(const FlowP& p, FlowW& w) {
   if (w.owed > 0) {
     __syncwarp();  // every lane's reads of the slot are complete before the async proxy overwrites it
-    fl_issue(p, w.gs, w.tab, w.it, w.ring, w.bars, w.pol_w, w.pol_kv);
+    fl_issue(p, w.gs, w.tab, w.it, (int)(threadIdx.x >> 5), w.ring, w.bars, w.pol_w, w.pol_kv);
     w.owed--;
   }
 }
-// tasks n .. n + cnt - 1 must have been posted: at most FL_SLOTS - cnt refills may be outstanding
-__device__ __forceinline__ void fl_ensure(const FlowP& p, FlowW& w, int cnt) {
-  while (w.owed > FL_SLOTS - cnt) fl_refill(p, w);
-}
 __device__ __forceinline__ const float* fl_ring_slot_at(const FlowW& w, int k) { return w.base + ((w.n + k) % FL_SLOTS) * FL_SLOT_FLOATS; }
+// non-blocking look at tasks n .. n + cnt - 1: issued before a phase polls its inputs so that the try_wait latency
+// (~200 cycles) overlaps the poll / RMSNorm; the blocking wait runs only if the tasks were not in yet
+__device__ __forceinline__ bool fl_ring_peek_n(const FlowP& p, FlowW& w, int cnt) {
+  while (w.owed > FL_SLOTS - cnt) fl_refill(p, w);
+  bool ok = true;
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+    if (k < cnt) { const int n = w.n + k; ok = fl_try_wait(w.bars + (n % FL_SLOTS) * 8, (uint32_t)(n / FL_SLOTS) & 1u) && ok; }
+  return ok;
+}
 // wait for tasks n .. n + cnt - 1 (cnt <= 3) with the try_waits in flight together
 __device__ __forceinline__ void fl_ring_wait_n(const FlowP& p, FlowW& w, int cnt, FlowWd& wd) {
-  fl_ensure(p, w, cnt);
+  while (w.owed > FL_SLOTS - cnt) fl_refill(p, w);
   uint32_t bar[3], par[3];
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
@@ -314,23 +331,16 @@ __device__ __forceinline__ void fl_ring_wait_n(const FlowP& p, FlowW& w, int cnt
     if (__any_sync(0xffffffffu, fl_giveup(wd, 0x120))) { wd.dead = 1; break; }
   }
 }
-// non-blocking look at tasks n .. n + cnt - 1: issued before a phase polls its inputs so that the try_wait latency
-// (~200 cycles) overlaps the poll / RMSNorm; the blocking wait runs only if the tasks were not in yet
-__device__ __forceinline__ bool fl_ring_peek_n(const FlowP& p, FlowW& w, int cnt) {
-  fl_ensure(p, w, cnt);
-  bool ok = true;
-#pragma unroll
-  for (int k = 0; k < 3; ++k)
-    if (k < cnt) { const int n = w.n + k; ok = fl_try_wait(w.bars + (n % FL_SLOTS) * 8, (uint32_t)(n / FL_SLOTS) & 1u) && ok; }
-  return ok;
-}
 __device__ __forceinline__ const float* fl_ring_wait(const FlowP& p, FlowW& w, FlowWd& wd) {
   fl_ring_wait_n(p, w, 1, wd);
   return fl_ring_slot_at(w, 0);
 }
-// Measured: paying the refills lazily inside the poll loops (one per failed poll) lengthens the poll period and made
-// the step 20-40 % slower; refilling eagerly AFTER the phase's stores is the better trade.
+// A consumed slot is refilled right after the stores of the phase that emptied it.  Posting the refills after the NEXT
+// phase's inputs were detected (to keep them out of the way of the polls) was measured too: 412 us/step against 321.
 __device__ __forceinline__ void fl_ring_release(const FlowP& p, FlowW& w) { w.n++; w.owed++; fl_refill(p, w); }
+__device__ __forceinline__ void fl_refill_all(const FlowP& p, FlowW& w) {
+  while (w.owed > 0) fl_refill(p, w);
+}
 
 // ---------------------------------------------------------------- phase helpers
 // Poll p.B x 768 LL words into xs (raw), zero rows >= B, block barrier.
@@ -362,7 +372,7 @@ __device__ __forceinline__ void fl_stage768(const FlowP& p, const unsigned long 
 #pragma unroll
     for (int k = 0; k < 3; ++k) xs[b * KC + tid + 256 * k] = (b < p.B && (rowmask == nullptr || rowmask[b])) ? ll_val(v[b][k]) : 0.f;
   }
-  __syncthreads();
+  fl_bar();
 }
 
 template <int BT>
@@ -399,13 +409,22 @@ __device__ __forceinline__ void fl_norm(float (&x)[BT][24], const float4 (&nw)[6
 // Norm weights come from HBM (they are part of the streamed blob) and the L1 returns loads in issue order: a register
 // load of them right before a poll made every X / XO edge wait for a DRAM round trip.  They are now fetched into shared
 // memory with cp.async half a layer ahead; this waits for the thread's own copies (the phase's barrier publishes them).
-__device__ __forceinline__ void fl_nw_fetch(float* dst, const float* src) {
-  if (threadIdx.x < KC / 4) cp_async16(dst + threadIdx.x * 4, src + threadIdx.x * 4);
-  asm volatile("cp.async.commit_group;" ::: "memory");
+// (The first version used cp.async, i.e. the LSU: its DRAM round trip then sat IN FRONT of the next phase's polls in the
+// L1's in-order return queue.)  One elected thread posts a 3 KiB bulk copy on a dedicated mbarrier; every consumer thread
+// waits for the barrier phase of the fetch it needs.
+__device__ __forceinline__ void fl_nw_fetch(float* dst, const float* src, uint64_t* bar, uint64_t pol) {
+  if (threadIdx.x == 0) {
+    fl_expect(smem_u32(bar), KC * 4);
+    fl_bulk(smem_u32(dst), src, KC * 4, smem_u32(bar), pol);
+  }
 }
-// groups complete in order; the attention / MLP halves always have exactly one younger fetch in flight behind the one they need
-__device__ __forceinline__ void fl_nw_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
-__device__ __forceinline__ void fl_nw_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fl_nw_wait(uint64_t* bar, int& count, FlowWd& wd) {
+  const uint32_t b = smem_u32(bar), parity = (uint32_t)count & 1u;
+  wd.spins = 0;
+  while (!fl_try_wait(b, parity))
+    if (__any_sync(0xffffffffu, fl_giveup(wd, 0x800))) { wd.dead = 1; break; }
+  count++;
+}
 __device__ __forceinline__ void fl_load_nw_s(const float* s_nw, float4 (&nw)[6], int lane) {
 #pragma unroll
   for (int i = 0; i < 6; ++i) nw[i] = reinterpret_cast<const float4*>(s_nw)[i * 32 + lane];
@@ -463,10 +482,11 @@ __device__ __forceinline__ void fl_bcast_store(unsigned long long* rep0, int R, 
 // k_sample's arithmetic with 256 threads: thread t plays the virtual threads t, t + 256, t + 512, t + 768 of the
 // 1024-thread kernel (virtual warp = warp + 8k, same lane) and every double-precision sum runs over the virtual warps
 // in k_sample's order, so the sampled index is bit for bit the one k_sample returns (sampler.cu:63-268).
-struct FlowSamp {
+struct __align__(16) FlowSamp {
   float x[FL_VPAD];
   uint32_t key[2][1024];
   double redd[32];
+  double pre[32];
   int redi[8];
   float redf[8];
   float bv[8];
@@ -480,12 +500,12 @@ __device__ __forceinline__ double fl_vsum_d(const double (&v)[4], double* redd) 
   double r[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) r[k] = warp_sum_d(v[k]);
-  __syncthreads();
+  fl_bar();
   if (lane == 0) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) redd[warp + 8 * k] = r[k];
   }
-  __syncthreads();
+  fl_bar();
   double t = 0.0;
 #pragma unroll 8
   for (int w = 0; w < 32; ++w) t += redd[w];  // fixed order => deterministic
@@ -494,9 +514,9 @@ __device__ __forceinline__ double fl_vsum_d(const double (&v)[4], double* redd) 
 __device__ __forceinline__ float fl_bmax(float v, float* redf) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   v = warp_max(v);
-  __syncthreads();
+  fl_bar();
   if (lane == 0) redf[warp] = v;
-  __syncthreads();
+  fl_bar();
   float t = -INFINITY;
 #pragma unroll
   for (int w = 0; w < FL_WARPS; ++w) t = fmaxf(t, redf[w]);
@@ -505,15 +525,21 @@ __device__ __forceinline__ float fl_bmax(float v, float* redf) {
 __device__ __forceinline__ int fl_bsum_i(int v, int* redi) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   v = __reduce_add_sync(0xffffffffu, v);
-  __syncthreads();
+  fl_bar();
   if (lane == 0) redi[warp] = v;
-  __syncthreads();
+  fl_bar();
   int t = 0;
 #pragma unroll
   for (int w = 0; w < FL_WARPS; ++w) t += redi[w];
   return t;
 }
-// bitonic sort of 1024 keys, ascending by virtual-thread index i = tid + 256 e; result left in key[] registers
+// Bitonic sort of 1024 keys.  Thread t holds the keys of positions 4t .. 4t+3: compare-exchange distances 1 and 2
+// stay in registers, 4 .. 64 are warp shuffles, only the six stages with distance >= 128 go through shared memory.
+// On return key[e] is the key of sorted position 4 * tid + e (ascending).
+__device__ __forceinline__ void fl_cx(uint32_t& a, uint32_t& b, bool up) {
+  const uint32_t lo = min(a, b), hi = max(a, b);
+  a = up ? lo : hi; b = up ? hi : lo;
+}
 __device__ __forceinline__ void fl_bitonic1024(uint32_t (&key)[4], uint32_t* buf0, uint32_t* buf1) {
   const int tid = threadIdx.x;
   int sb = 0;
@@ -521,39 +547,29 @@ __device__ __forceinline__ void fl_bitonic1024(uint32_t (&key)[4], uint32_t* buf
   for (int k = 2; k <= 1024; k <<= 1) {
 #pragma unroll 1
     for (int j = k >> 1; j > 0; j >>= 1) {
-      if (j >= 256) {  // partner in the same thread
-        const bool up0 = ((tid) & k) == 0, up1 = ((tid + 256) & k) == 0, up2 = ((tid + 512) & k) == 0;
-        if (j == 256) {  // pairs (0,1), (2,3)
-          uint32_t lo = min(key[0], key[1]), hi = max(key[0], key[1]);
-          key[0] = up0 ? lo : hi; key[1] = up0 ? hi : lo;
-          lo = min(key[2], key[3]); hi = max(key[2], key[3]);
-          key[2] = up2 ? lo : hi; key[3] = up2 ? hi : lo;
-        } else {         // j == 512: pairs (0,2), (1,3)
-          uint32_t lo = min(key[0], key[2]), hi = max(key[0], key[2]);
-          key[0] = up0 ? lo : hi; key[2] = up0 ? hi : lo;
-          lo = min(key[1], key[3]); hi = max(key[1], key[3]);
-          key[1] = up1 ? lo : hi; key[3] = up1 ? hi : lo;
-        }
-        continue;
-      }
-      uint32_t other[4];
-      if (j >= 32) {
-        uint32_t* buf = sb ? buf1 : buf0;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) buf[tid + 256 * e] = key[e];
-        __syncthreads();
-#pragma unroll
-        for (int e = 0; e < 4; ++e) other[e] = buf[(tid + 256 * e) ^ j];
-        sb ^= 1;
+      if (j == 1) {
+        fl_cx(key[0], key[1], ((4 * tid) & k) == 0);
+        fl_cx(key[2], key[3], ((4 * tid + 2) & k) == 0);
+      } else if (j == 2) {
+        fl_cx(key[0], key[2], ((4 * tid) & k) == 0);
+        fl_cx(key[1], key[3], ((4 * tid + 1) & k) == 0);
       } else {
+        const int d = j >> 2;  // partner thread distance
+        uint32_t other[4];
+        if (d >= 32) {
+          uint32_t* buf = sb ? buf1 : buf0;
+          *reinterpret_cast<uint4*>(buf + 4 * tid) = make_uint4(key[0], key[1], key[2], key[3]);
+          fl_bar();
+          const uint4 o = *reinterpret_cast<const uint4*>(buf + 4 * (tid ^ d));
+          other[0] = o.x; other[1] = o.y; other[2] = o.z; other[3] = o.w;
+          sb ^= 1;
+        } else {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) other[e] = __shfl_xor_sync(0xffffffffu, key[e], j);
-      }
+          for (int e = 0; e < 4; ++e) other[e] = __shfl_xor_sync(0xffffffffu, key[e], d);
+        }
+        const bool up = ((4 * tid) & k) == 0, lower = (tid & d) == 0;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int i = tid + 256 * e;
-        const bool up = (i & k) == 0, lower = (i & j) == 0;
-        key[e] = (lower == up) ? min(key[e], other[e]) : max(key[e], other[e]);
+        for (int e = 0; e < 4; ++e) key[e] = (lower == up) ? min(key[e], other[e]) : max(key[e], other[e]);
       }
     }
   }
@@ -568,17 +584,37 @@ __device__ __noinline__ int fl_sample_row(const ctb_sampler_config& c, const flo
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool pen = c.penalty_on && row < c.penalty_max_ids;
   const float temp = c.temperature[qi];
-  for (int v = tid; v < V; v += FL_THREADS) {
-    float x = __fdiv_rn(sm.x[v], temp);
-    if (pen) {
-      int cnt = 0;
-      for (int w = 0; w < nwin; ++w) cnt += (sm.win[w] == v);
-      const float a = c.penalty_lut[cnt];
-      x = (x < 0.f) ? __fmul_rn(x, a) : __fdiv_rn(x, a);
-    }
-    sm.x[v] = x;
+  float qn[4];  // Exp(1) noise of this thread's elements, requested now and used by the final arg-max
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int v = tid + 256 * k;
+    qn[k] = (q_noise != nullptr && v < V) ? __ldg(q_noise + (size_t)row * V + v) : 1.f;
   }
-  __syncthreads();
+  {
+    float xr[4];
+    int cnt[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const int v = tid + 256 * k; xr[k] = v < V ? __fdiv_rn(sm.x[v], temp) : 0.f; }
+    if (pen) {
+#pragma unroll 4
+      for (int w = 0; w < nwin; ++w) {
+        const int id = sm.win[w];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) cnt[k] += (id == tid + 256 * k);
+      }
+    }
+    fl_bar();  // every raw logit has been read
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int v = tid + 256 * k;
+      if (v < V) {
+        float x = xr[k];
+        if (pen) { const float a = c.penalty_lut[cnt[k]]; x = (x < 0.f) ? __fmul_rn(x, a) : __fdiv_rn(x, a); }
+        sm.x[v] = x;
+      }
+    }
+  }
+  fl_bar();
   float mx = -INFINITY;
   for (int v = tid; v < V; v += FL_THREADS) mx = fmaxf(mx, sm.x[v]);
   mx = fl_bmax(mx, sm.redf);
@@ -604,11 +640,12 @@ __device__ __noinline__ int fl_sample_row(const ctb_sampler_config& c, const flo
     for (int k = 0; k < 4; ++k) { const int vt = tid + 256 * k; key[k] = vt < V ? float_key(sm.x[vt]) : 0u; }
     fl_bitonic1024(key, sm.key[0], sm.key[1]);
     FL_SK();
-    __syncthreads();
+    fl_bar();
     uint32_t* skey = sm.key[0];
+    *reinterpret_cast<uint4*>(skey + 4 * tid) = make_uint4(key[0], key[1], key[2], key[3]);  // sorted position 4 tid + e
+    fl_bar();
 #pragma unroll
-    for (int k = 0; k < 4; ++k) skey[tid + 256 * k] = key[k];
-    __syncthreads();
+    for (int k = 0; k < 4; ++k) key[k] = skey[tid + 256 * k];  // back to k_sample's one-key-per-virtual-thread view
     uint32_t t_p = 0;
     if (use_p) {
       double inc[4];
@@ -623,18 +660,22 @@ __device__ __noinline__ int fl_sample_row(const ctb_sampler_config& c, const flo
         }
         inc[k] = a;
       }
-      __syncthreads();
+      fl_bar();
       if (lane == 31) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) sm.redd[warp + 8 * k] = inc[k];
       }
-      __syncthreads();
+      fl_bar();
+      if (tid == 0) {  // exclusive prefix over the 32 virtual warps, added in k_sample's order (w = 0, 1, ...)
+        double run = 0.0;
+        for (int w = 0; w < 32; ++w) { const double t = sm.redd[w]; sm.pre[w] = run; run += t; }
+      }
+      fl_bar();
       int removed = 0;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int vw = warp + 8 * k, vt = tid + 256 * k;
-        double base = 0.0;
-        for (int w = 0; w < vw; ++w) base += sm.redd[w];
+        const double base = sm.pre[vw];
         const float cum = (float)(base + inc[k]);
         removed += ((cum <= pthr) && (vt < 1024 - min_keep)) ? 1 : 0;
       }
@@ -652,7 +693,7 @@ __device__ __noinline__ int fl_sample_row(const ctb_sampler_config& c, const flo
     gm = fl_bmax(gm, sm.redf);
     thr_key = float_key(gm);
   }
-  __syncthreads();  // every read of sm.key / sm.x above is complete
+  fl_bar();  // every read of sm.key / sm.x above is complete
   const bool ban = step < c.min_new_token;
   float mx2 = -INFINITY;
   for (int v = tid; v < V; v += FL_THREADS) {
@@ -669,26 +710,30 @@ __device__ __noinline__ int fl_sample_row(const ctb_sampler_config& c, const flo
   FL_SK();
   float best = -1.f;
   int besti = 0x7fffffff;
-  for (int v = tid; v < V; v += FL_THREADS) {
-    const float pr = __fdiv_rn(expf(sm.x[v] - mx2), den2f);
-    const float qn = q_noise ? q_noise[(size_t)row * V + v] : philox_exp1(c.philox_seed, (uint32_t)row, (uint32_t)v, (uint32_t)step);
-    const float r = __fdiv_rn(pr, qn);
-    if (r > best) { best = r; besti = v; }  // ascending v within a thread: first max wins
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int v = tid + 256 * k;
+    if (v < V) {
+      const float pr = __fdiv_rn(expf(sm.x[v] - mx2), den2f);
+      const float qv = q_noise ? qn[k] : philox_exp1(c.philox_seed, (uint32_t)row, (uint32_t)v, (uint32_t)step);
+      const float r = __fdiv_rn(pr, qv);
+      if (r > best) { best = r; besti = v; }  // ascending v within a thread: first max wins
+    }
   }
   for (int o = 16; o > 0; o >>= 1) {
     const float ob = __shfl_xor_sync(0xffffffffu, best, o);
     const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
     if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
   }
-  __syncthreads();
+  fl_bar();
   if (lane == 0) { sm.bv[warp] = best; sm.bi[warp] = besti; }
-  __syncthreads();
+  fl_bar();
   if (tid == 0) {
     for (int w = 1; w < FL_WARPS; ++w)
       if (sm.bv[w] > best || (sm.bv[w] == best && sm.bi[w] < besti)) { best = sm.bv[w]; besti = sm.bi[w]; }
     sm.out = besti < V ? besti : 0;  // all-NaN row: ATen argmax returns the first index
   }
-  __syncthreads();
+  fl_bar();
   FL_SK();
 #undef FL_SK
   return sm.out;
@@ -699,6 +744,7 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_flow(const __grid_constant__ 
   extern __shared__ __align__(128) unsigned char fl_smem[];
   float* xs = reinterpret_cast<float*>(fl_smem + FL_RING_BYTES);  // [BT][768]
   __shared__ __align__(8) uint64_t s_bar[FL_WARPS * FL_SLOTS];
+  __shared__ __align__(8) uint64_t s_nwbar[2];  // norm-weight fetches (attention half, MLP half)
   __shared__ int s_pos[BT], s_active[BT], s_page[BT];
   __shared__ float s_cos[BT * 64], s_sin[BT * 64];
   __shared__ float s_red[FL_ROWS][FL_WARPS][BT];
@@ -714,6 +760,7 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_flow(const __grid_constant__ 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int LPB = 32 / BT;
   if (tid < FL_WARPS * FL_SLOTS) mbar_init(&s_bar[tid], 1);
+  if (tid < 2) mbar_init(&s_nwbar[tid], 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
   pdl_trigger();
@@ -752,6 +799,7 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_flow(const __grid_constant__ 
   uint64_t pol_w, pol_kv;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_w));
   asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_kv));
+  int nw1_cnt = 0, nw2_cnt = 0;  // completed waits on the two norm-weight barriers (their phase parity)
   FlowW fw;
   fw.base = reinterpret_cast<float*>(fl_smem) + (size_t)warp * FL_SLOTS * FL_SLOT_FLOATS;
   fw.ring = smem_u32(fw.base);
@@ -766,7 +814,7 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_flow(const __grid_constant__ 
   const int myrep = g.cta % R;
   const int o_row = g.cta + g.G * warp;  // this warp's O-proj row (valid iff fl_o_valid)
   unsigned long long* tailw = p.arena + (size_t)FL_RMAX * FL_REP_STRIDE;  // parity-0 tail: q/k/v words, logits, ids
-  __syncthreads();
+  fl_bar();
 
   // the repetition window of this CTA's sampler row: the last <= past_window ids of (item, codebook)
   int nwin = 0;
@@ -796,11 +844,11 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_flow(const __grid_constant__ 
       }                                                                                                                 \
     }                                                                                                                   \
     if (tid == 0) s_geo = g;                                                                                            \
-    __syncthreads();                                                                                                    \
-    fw.it.l = 0; fw.it.k = 0; fw.it.hsub = 0;                                                                           \
+    fl_bar();                                                                                                           \
+    fw.it.l = 0; fw.it.k = 0; fw.it.hsub = 0; fw.owed = 0;                                                              \
     fw.it.ntab = fl_build_table(p, &s_geo, s_tab[warp]);                                                                \
     __syncwarp();                                                                                                       \
-    for (int k_ = 0; k_ < FL_SLOTS; ++k_) fl_issue(p, fw.gs, fw.tab, fw.it, fw.ring, fw.bars, pol_w, pol_kv);           \
+    for (int k_ = 0; k_ < FL_SLOTS; ++k_) fl_issue(p, fw.gs, fw.tab, fw.it, warp, fw.ring, fw.bars, pol_w, pol_kv);     \
     for (int i = tid; i < BT * 64; i += FL_THREADS) {                                                                   \
       const int b = i / 64;                                                                                             \
       s_cos[i] = b < p.B ? __ldg(p.W + p.o_cos + (size_t)s_pos[b] * 64 + (i % 64)) : 0.f;                               \
@@ -814,8 +862,8 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_flow(const __grid_constant__ 
   for (int sidx = 0;; ++sidx) {
   // ======================================================================== one decode step
   FL_TRACE();
-  fl_nw_fetch(s_nw1, p.W + p.layer0 + p.o_ln1);
-  fl_nw_fetch(s_nw2, p.W + p.layer0 + p.o_ln2);
+  fl_nw_fetch(s_nw1, p.W + p.layer0 + p.o_ln1, &s_nwbar[0], pol_w);
+  fl_nw_fetch(s_nw2, p.W + p.layer0 + p.o_ln2, &s_nwbar[1], pol_w);
   {  // step input: prompt column or sum of the code embeddings; every load of the thread in flight together
     float ev[BT * 3][8];
 #pragma unroll
@@ -847,7 +895,7 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_flow(const __grid_constant__ 
       xs[tid + it_ * FL_THREADS] = v;
     }
   }
-  __syncthreads();
+  fl_bar();
   FL_TRACE();
 
   for (int l = 0; l < p.L; ++l) {
@@ -862,11 +910,12 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_flow(const __grid_constant__ 
     {
       float4 nw[6];
       FL_EV(0);
-      fl_nw_wait1();
+      fl_nw_wait(&s_nwbar[0], nw1_cnt, wd);
       const bool q_rdy = fl_ring_peek_n(p, fw, 1);
       if (l > 0) fl_stage768<BT>(p, myr + FL_A_X, tagl + FT_X, xs, wd, fw);
-      else __syncthreads();
+      else fl_bar();
       FL_EV(1);
+      fl_refill_all(p, fw);
       fl_load_nw_s(s_nw1, nw, lane);
       float x[BT][24];
       fl_load_x<BT>(xs, x, lane);
@@ -954,7 +1003,7 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_flow(const __grid_constant__ 
 #pragma unroll
             for (int k = 0; k < 8; ++k) q[k] = ll_val(w[k]);
           }
-          if (sb == 0) FL_EV(4);
+          if (sb == 0) { FL_EV(4); fl_refill_all(p, fw); }
           // the token of THIS step: its K/V rows arrive from the QKV phase through the LL region, not the cache
           {
             const bool mine0 = (tbase == pos), mine1 = (tbase + 4 == pos);
@@ -1021,13 +1070,13 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_flow(const __grid_constant__ 
             if (fl_kv_more(g, sb + 1, nxt)) fl_ring_release(p, fw);
             else pend_kv = 1;  // last chunk: refill after the partial has been stored
           }
-          __syncthreads();  // previous chunk's merge no longer reads s_ao / s_am / s_al
+          fl_bar();  // previous chunk's merge no longer reads s_ao / s_am / s_al
           if (lane < 8) {
             *reinterpret_cast<float4*>(&s_ao[warp][lane * 8]) = make_float4(o[0], o[1], o[2], o[3]);
             *reinterpret_cast<float4*>(&s_ao[warp][lane * 8 + 4]) = make_float4(o[4], o[5], o[6], o[7]);
             if (lane == 0) { s_am[warp] = m; s_al[warp] = lsum; }
           }
-          __syncthreads();
+          fl_bar();
           if (tid < 64) {
             float cm = M;
 #pragma unroll
@@ -1095,10 +1144,11 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_flow(const __grid_constant__ 
       FL_EV(5);
 
       // ============ C: O-proj + residual on the merged attention output ============
-      __syncthreads();  // xs (raw x) is no longer read by any warp of this CTA
-      fl_nw_fetch(s_nw1, l + 1 < p.L ? Wl + p.layer_stride + p.o_ln1 : p.W + p.o_final_norm);
+      fl_bar();  // xs (raw x) is no longer read by any warp of this CTA
+      if (l + 1 < p.L || p.sample) fl_nw_fetch(s_nw1, l + 1 < p.L ? Wl + p.layer_stride + p.o_ln1 : p.W + p.o_final_norm, &s_nwbar[0], pol_w);
       const bool o_rdy = fl_o_valid(g) ? fl_ring_peek_n(p, fw, 1) : true;
       fl_stage768<BT>(p, myr + FL_A_AO, tagl + FT_AO, xs, wd, fw, s_active);
+      fl_refill_all(p, fw);
       FL_EV(6);
       if (fl_o_valid(g)) {
         fl_load_x<BT>(xs, x, lane);
@@ -1119,14 +1169,15 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_flow(const __grid_constant__ 
     // ============ D: gate/up + SiLU * mul ============
     {
       float4 nw[6];
-      fl_nw_wait1();
+      fl_nw_wait(&s_nwbar[1], nw2_cnt, wd);
       int ngu = 0;
 #pragma unroll
       for (int j = 0; j < FL_GU; ++j) ngu += fl_gu_valid(g, j, p.I) ? 1 : 0;
       const bool gu_rdy = fl_ring_peek_n(p, fw, ngu);
-      __syncthreads();  // every warp is done with xs (attention output)
+      fl_bar();  // every warp is done with xs (attention output)
       FL_CK(8);
       fl_stage768<BT>(p, myr + FL_A_XO, tagl + FT_XO, xs, wd, fw);
+      fl_refill_all(p, fw);
       fl_load_nw_s(s_nw2, nw, lane);
       FL_EV(9);
       FL_CK(9);
@@ -1210,10 +1261,15 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_flow(const __grid_constant__ 
             // bumped with red.add by the producers were tried instead of the sentinel words: no faster, 356 vs 352 us.)
             wd.spins = 0;
             bool sentinel_ok = false;
+            int it_s = 0, it_f = 0;
+            if (b == 0) FL_CK(12);
             while (true) {
+              ++it_s;
               ll_ld2(ap + lane * 4, w[0], w[1]);
               if (sentinel_ok || __all_sync(0xffffffffu, ll_tag(w[0]) == tagl + FT_ACT && ll_tag(w[1]) == tagl + FT_ACT)) {
+                if (!sentinel_ok && b == 0) FL_CK(13);
                 sentinel_ok = true;
+                ++it_f;
                 bool ok = ll_tag(w[0]) == tagl + FT_ACT && ll_tag(w[1]) == tagl + FT_ACT;
                 ll_ld2(ap + lane * 4 + 2, w[2], w[3]);
 #pragma unroll
@@ -1227,12 +1283,14 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_flow(const __grid_constant__ 
               }
               if (__any_sync(0xffffffffu, fl_giveup(wd, 0x500))) { wd.dead = 1; break; }
             }
+            if (b == 0) { FL_CK(14); if (p.trace && l == 10 && tid == 0 && blockIdx.x == 0) { p.trace[3015] = it_s; p.trace[3016] = it_f; } }
 #pragma unroll
             for (int k = 0; k < 12; ++k) xd[b][k] = ll_val(w[k]);
           }
         }
       }
       FL_EV(11);
+      fl_refill_all(p, fw);
       int e_tasks = 0;
       {
         // both down tasks (<= 6 row slices) together, one butterfly, refills after the partial sums are in shared memory
@@ -1266,8 +1324,8 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_flow(const __grid_constant__ 
         e_tasks = nr1 > 0 ? 2 : 1;
       }
       FL_EV(12);
-      __syncthreads();
-      if (l + 1 < p.L) fl_nw_fetch(s_nw2, Wl + p.layer_stride + p.o_ln2);
+      fl_bar();
+      if (l + 1 < p.L) fl_nw_fetch(s_nw2, Wl + p.layer_stride + p.o_ln2, &s_nwbar[1], pol_w);
       if (tid < FL_ROWS * BT * 8) {  // K slices summed in the order 0..7 (deterministic); 8 threads share an element's replicas
         const int e = tid >> 3, b = e % BT, j = e / BT, row = g.cta + g.G * j;
         if (row < KC && b < p.B) {
@@ -1289,9 +1347,10 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_flow(const __grid_constant__ 
   if (p.sample) {
     const unsigned long long* myr = p.arena + (size_t)(p.L & 1) * FL_PARITY_WORDS + (size_t)myrep * FL_REP_STRIDE;
     float4 nw[6];
-    fl_nw_wait();
-    __syncthreads();
+    fl_nw_wait(&s_nwbar[0], nw1_cnt, wd);
+    fl_bar();
     fl_stage768<BT>(p, myr + FL_A_X, base + 8u * (uint32_t)p.L + FT_X, xs, wd, fw);
+    fl_refill_all(p, fw);
     fl_load_nw_s(s_nw1, nw, lane);
     float x[BT][24];
     fl_load_x<BT>(xs, x, lane);
@@ -1330,9 +1389,9 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_flow(const __grid_constant__ 
     }
   }
   FL_TRACE();
-  __syncthreads();
+  fl_bar();
   if (tid < p.B && s_active[tid]) s_pos[tid]++;   // positions advance once per step
-  __syncthreads();
+  fl_bar();
   const bool more = ink && sidx + 1 < p.nsteps;
   if (more) FL_PREP_STEP();
   if constexpr (INK) {
@@ -1355,7 +1414,7 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_flow(const __grid_constant__ 
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           if (tid + 256 * k < p.V) s_samp.x[tid + 256 * k] = ll_val(w[k]);
-        __syncthreads();
+        fl_bar();
         const int id = fl_sample_row(p.samp, p.q_noise, s_samp, p.V, row, qi, nwin, lstep, (p.trace && row == 0) ? p.trace + 3100 : nullptr);
         if (tid == 0) {
           ll_st(tailw + FL_A_IDX + row, __int_as_float(id), tagi);
@@ -1366,7 +1425,7 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_flow(const __grid_constant__ 
           }
         }
         if (p.samp.penalty_on && row < p.samp.penalty_max_ids && nwin < p.samp.past_window) nwin++;
-        __syncthreads();
+        fl_bar();
       }
       FL_TRACE();
       // ============ finish / write-back / counters (gpt.py:512-525,572-577) - every CTA keeps the loop state ============
@@ -1380,7 +1439,7 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_flow(const __grid_constant__ 
         }
         s_ids[(tid / p.rows_per_item) * 8 + tid % p.rows_per_item] = __float_as_int(ll_val(w));
       }
-      __syncthreads();
+      fl_bar();
       if (tid == 0) {
         int notall = 0;
         for (int b = 0; b < p.B; ++b) {
@@ -1403,7 +1462,7 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_flow(const __grid_constant__ 
           p.st->step = lstep + 1;
         }
       }
-      __syncthreads();
+      fl_bar();
       FL_TRACE();
     }
   }

@@ -607,7 +607,7 @@ static int launch_step_flow_t(const FlowP& fp, cudaStream_t s) {
   const size_t smem = (size_t)FL_RING_BYTES + (size_t)BT * KC * sizeof(float);
   { int rc = ensure_smem_attr((const void*)k_flow<BT>, (int)smem); if (rc) return rc; }
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(g_num_sms); cfg.blockDim = dim3(FL_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cfg.gridDim = dim3(g_num_sms); cfg.blockDim = dim3(FL_LAUNCH_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeCooperative;  // every CTA must be resident: CTAs wait for each other's words
   attr[0].val.cooperative = 1;
@@ -719,6 +719,13 @@ extern "C" int ctb_gpt_profile_kernel(ctb_gpt* h, int32_t kind, void* stream) {
   int rc;
   if (kind == 5) return h->use_tc ? launch_heads_tc(h, s) : launch_heads(h, x, s);
   if (kind == 6) return launch_sampler(h, x, s);
+  if (kind == 8) {  // 16 decode iterations in ONE launch of the dataflow step kernel (sampling tail inside)
+    if (!flow_ink(h)) return set_err(CTB_ERR_STATE, "multi-step dataflow kernel unavailable for this handle/batch");
+    if (h->steps_enqueued + 16 > h->max_new || h->T0 + h->steps_enqueued + 16 > h->cfg.max_context)
+      return set_err(CTB_ERR_STATE, "no room for 16 more steps (max_new / max_context reached)");
+    h->steps_enqueued += 16;
+    return launch_step_flow(h, -1, true, s, 16);
+  }
   if (kind == 7) {  // the one-kernel decode step alone (context grows by one token per call)
     if (h->steps_enqueued >= h->max_new || h->T0 + h->steps_enqueued >= h->cfg.max_context)
       return set_err(CTB_ERR_STATE, "no room for another step (max_new / max_context reached)");

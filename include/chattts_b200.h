@@ -140,7 +140,8 @@ int ctb_gpt_status_query(ctb_gpt* h, ctb_gpt_status* out, int32_t* end_idx_host,
 
 /* Measurement hook for bench.py's roofline: launches ONE kernel kind once per layer on the
  * state left by the last generate call (kind 0 qkv, 1 attention, 2 o-proj, 3 gate/up, 4 down;
- * 5 = heads, 6 = sampler, 7 = the one-kernel decode step k_step: one launch).  No reference counterpart. */
+ * 5 = heads, 6 = sampler, 7 = one decode step as ONE kernel launch (k_flow / k_step), 8 = 16 decode steps in one
+ * k_flow launch with the sampling tail inside).  7 and 8 advance the generation.  No reference counterpart. */
 int ctb_gpt_profile_kernel(ctb_gpt* h, int32_t kind, void* stream);
 
 /* Profiling aid: with CTB_MEGA_TRACE=1 in the environment at ctb_gpt_create, the one-kernel decode step records

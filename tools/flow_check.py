@@ -148,6 +148,8 @@ def main():
     print("  GU (all tasks) of CTA0/warp0, cycles: wait=%d dot=%d reduce=%d silu+store=%d release=%d | stage=%d load_x=%d norm=%d" % (
         ck[1] - ck[0], ck[2] - ck[1], ck[3] - ck[2], ck[5] - ck[3], ck[6] - ck[5], ck[9] - ck[8], ck[10] - ck[9], ck[11] - ck[10]))
     print("  L2 probe (cycles per 8 dependent loads): relaxed.gpu=%d ldcg=%d volatile=%d | 8 stores issue=%d" % tuple(int(buf2[3020 + k]) for k in range(4)))
+    print("  ACT poll of CTA0/warp0, cycles: enter->sentinel=%d sentinel->full=%d  iterations: sentinel=%d full=%d" % (
+        int(buf2[3013]) - int(buf2[3012]), int(buf2[3014]) - int(buf2[3013]), int(buf2[3015]), int(buf2[3016])))
     print("  CTA 0:", (ev[0] - t0).tolist())
     print("  CTA 100:", (ev[100] - t0).tolist())
     print("  CTA 147:", (ev[147] - t0).tolist(), flush=True)
