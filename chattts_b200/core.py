@@ -19,7 +19,7 @@ import numpy as np
 import torch
 
 from .config import Config
-from .decoder import DVAE, Vocos, decode_to_wavs
+from .decoder import decode_to_wavs_window, DVAE, Vocos, decode_to_wavs
 from .embed import Embed
 from .gpt import GPT
 from .processors import gen_logits
@@ -90,7 +90,7 @@ class Chat:
                                 coef=coef)
 
     def load_states(self, states: Dict[str, Dict[str, torch.Tensor]], tokenizer, speaker, device=None, coef=None,
-                    max_batch: int = 32, max_context: int = 2560, weights_blob: Optional[torch.Tensor] = None) -> bool:
+                    max_batch: int = 32, max_context: int = 4096, weights_blob: Optional[torch.Tensor] = None) -> bool:
         """Build every model from in-memory state dicts (reference names) - core.py:275-384."""
         device = torch.device(device or "cuda")
         self.device = self.device_gpt = device
@@ -218,19 +218,27 @@ class Chat:
         for i in range(n):
             chunk = text[i * max_split_batch: (i + 1) * max_split_batch]
             for result in self._infer_code(chunk, stream, self.device, use_decoder, params_infer_code):
-                wavs = self._decode_to_wavs(result.hiddens if use_decoder else result.ids, use_decoder)
-                result.destroy()
+                res = result.hiddens if use_decoder else result.ids
                 if stream:
+                    # core.py:455-503 decodes the CUMULATIVE sequence at every yield and slices [length, length +
+                    # stream_speed) out of it; the same samples are produced here from the token window they depend on
+                    # (decoder.decode_to_wavs_window)
                     pass_batch_count += 1
+                    last = [r.clone() for r in res]
+                    total = 512 * max(int(r.size(0)) for r in res) - 256
+                    result.destroy()
                     if pass_batch_count <= params_infer_code.pass_first_n_batches:
                         continue
-                    a, b = length, min(length + params_infer_code.stream_speed, wavs.shape[1])
+                    a, b = length, min(length + params_infer_code.stream_speed, total)
                     length = b
-                    yield wavs[:, a:b]
+                    yield self._decode_window(last, use_decoder, a, b)
                 else:
+                    wavs = self._decode_to_wavs(res, use_decoder)
+                    result.destroy()
                     yield wavs
             if stream:
-                new_wavs = wavs[:, length:]
+                total = 512 * max(int(r.size(0)) for r in last) - 256
+                new_wavs = self._decode_window(last, use_decoder, length, total)
                 keep = np.sum(np.abs(new_wavs) > 1e-5, axis=0) > 0
                 yield new_wavs[:][:, keep]
 
@@ -238,6 +246,11 @@ class Chat:
     @torch.inference_mode()
     def _decode_to_wavs(self, result_list: List[torch.Tensor], use_decoder: bool):
         return decode_to_wavs(result_list, use_decoder, self.decoder, self.dvae)
+
+    @torch.inference_mode()
+    def _decode_window(self, result_list: List[torch.Tensor], use_decoder: bool, a: int, b: int) -> np.ndarray:
+        """Samples [a, b) of ``_decode_to_wavs(result_list)`` from the tokens they depend on (streaming hand-off)."""
+        return decode_to_wavs_window(result_list, use_decoder, self.decoder, self.dvae, a, b)
 
     def _vocos_decode(self, spec: torch.Tensor) -> np.ndarray:
         return self.vocos_engine().vocos_decode(spec).cpu().numpy()

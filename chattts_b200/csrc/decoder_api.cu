@@ -82,6 +82,7 @@ struct ctb_decoder {
   const float* vW;
   int max_batch, max_tokens;
   size_t max_rows;  // max_batch * 2 * max_tokens frames
+  size_t cap_rows;  // frames the activation buffers currently hold
   float *bufA, *bufB, *bufH, *mel_tm, *staged_in;
   // tcgen05 path: tf32-rounded hi / lo copies of both blobs (same offsets as the fp32 blobs)
   float *dW_hi, *dW_lo, *vW_hi, *vW_lo;
@@ -96,6 +97,33 @@ extern "C" int ctb_decoder_destroy(ctb_decoder* h) {
   void* ptrs[] = {h->bufA, h->bufB, h->bufH, h->mel_tm, h->staged_in, h->dW_hi, h->dW_lo, h->vW_hi, h->vW_lo};
   for (void* p : ptrs) if (p) cudaFree(p);
   delete h;
+  return CTB_OK;
+}
+
+// grow the activation buffers to `rows` frames (time-major [rows, C]); the contents are scratch
+static int dec_reserve(ctb_decoder* h, size_t rows, cudaStream_t s) {
+  if (rows <= h->cap_rows) return CTB_OK;
+  CTB_CUDA(cudaStreamSynchronize(s));
+  float** bufs[] = {&h->bufA, &h->bufB, &h->bufH, &h->mel_tm, &h->staged_in};
+  for (float** b : bufs) if (*b) { cudaFree(*b); *b = nullptr; }
+  h->cap_rows = 0;
+  const ctb_convstack_config& dc = h->dc;
+  const ctb_vocos_config& vc = h->vc;
+  const size_t R = std::min(h->max_rows, rows + rows / 8);
+  const size_t wide = std::max((size_t)std::max(4 * dc.hidden, vc.intermediate_dim), (size_t)vc.n_fft);
+  const size_t narrow = std::max((size_t)std::max(std::max(dc.hidden, dc.idim), vc.dim), (size_t)dc.odim);
+  cudaError_t e = cudaSuccess;
+  auto A = [&](float** p, size_t n) { if (e == cudaSuccess) e = cudaMalloc((void**)p, n * sizeof(float)); };
+  A(&h->bufA, R * std::max(narrow, (size_t)spec_k(vc)));
+  A(&h->bufB, R * narrow);
+  A(&h->bufH, R * wide);
+  A(&h->mel_tm, R * MEL_PAD);
+  A(&h->staged_in, R * dc.idim);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return set_err(CTB_ERR_NOMEM, "decoder buffers for %zu frames: %s", R, cudaGetErrorString(e));
+  }
+  h->cap_rows = R;
   return CTB_OK;
 }
 
@@ -121,16 +149,9 @@ extern "C" int ctb_decoder_create(const ctb_convstack_config* dc, const float* d
   h->dW = dvae_blob_dev; h->vW = vocos_blob_dev;
   h->max_batch = max_batch; h->max_tokens = max_tokens;
   h->max_rows = (size_t)max_batch * 2 * max_tokens;
-  const size_t R = h->max_rows;
-  const size_t wide = std::max((size_t)std::max(4 * dc->hidden, vc->intermediate_dim), (size_t)vc->n_fft);
-  const size_t narrow = std::max((size_t)std::max(std::max(dc->hidden, dc->idim), vc->dim), (size_t)dc->odim);
   cudaError_t e = cudaSuccess;
   auto A = [&](float** p, size_t n) { if (e == cudaSuccess) e = cudaMalloc((void**)p, n * sizeof(float)); };
-  A(&h->bufA, R * std::max(narrow, (size_t)spec_k(*vc)));
-  A(&h->bufB, R * narrow);
-  A(&h->bufH, R * wide);
-  A(&h->mel_tm, R * MEL_PAD);
-  A(&h->staged_in, R * dc->idim);
+  // activation buffers are sized by the largest call seen so far (dec_reserve), not by max_batch x max_tokens
   h->use_tc = getenv("CTB_DECODER_FMA") == nullptr;
   if (h->use_tc) {
     if (h->dW) { A(&h->dW_hi, h->dl.total); A(&h->dW_lo, h->dl.total); }
@@ -291,6 +312,7 @@ extern "C" int ctb_dvae_decode(ctb_decoder* h, const void* in_dev, int32_t in_la
     return set_err(CTB_ERR_ARG, "B=%d x T=%d exceeds this handle (max_batch=%d, max_tokens=%d)", B, T, h->max_batch,
                    h->max_tokens);
   if (in_layout < 0 || in_layout > 2) return set_err(CTB_ERR_ARG, "bad in_layout");
+  { int rc = dec_reserve(h, (size_t)B * 2 * T, (cudaStream_t)stream); if (rc) return rc; }
   return dvae_run(h, in_dev, in_layout, B, T, mel_dev, (cudaStream_t)stream);
 }
 
@@ -299,5 +321,8 @@ extern "C" int ctb_vocos_decode(ctb_decoder* h, const float* mel_dev, int32_t B,
   if (!h || !wav_dev) return set_err(CTB_ERR_ARG, "null argument");
   if (!h->vW) return set_err(CTB_ERR_STATE, "handle was created without Vocos weights");
   if (B < 1 || F < 2 || (size_t)B * F > h->max_rows) return set_err(CTB_ERR_ARG, "B x F exceeds this handle");
+  if (mel_dev == nullptr && (size_t)B * F > h->cap_rows)
+    return set_err(CTB_ERR_STATE, "no mel of this shape was left in the handle by ctb_dvae_decode");
+  { int rc = dec_reserve(h, (size_t)B * F, (cudaStream_t)stream); if (rc) return rc; }
   return vocos_run(h, mel_dev, B, F, wav_dev, (cudaStream_t)stream);
 }

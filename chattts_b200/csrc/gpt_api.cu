@@ -54,6 +54,8 @@ struct ctb_gpt {
   uint8_t *active, *finish;
   LoopState* st;
   size_t kv_layer_floats;
+  size_t kv_pages;      // pages per layer currently in the pool
+  int bt_B; size_t bt_per_row;  // shape the uploaded block table was built for
   // per generate() call
   int B, T0, max_new, infer_text, started;
   ctb_sampler_config sampler;
@@ -263,8 +265,9 @@ extern "C" int ctb_gpt_create(const ctb_gpt_config* c, const float* weights_dev,
   TRY(dalloc(&h->mlp, Bp * c->intermediate_size));
   const size_t nlog = std::max((size_t)c->num_vq * c->num_audio_tokens, (size_t)c->num_text_tokens);
   TRY(dalloc(&h->logits, Bp * nlog));
-  h->kv_layer_floats = (size_t)c->max_batch * h->pages_per_row * 2 * c->num_kv_heads * kPageTokens * c->head_dim;
-  TRY(dalloc(&h->kv, h->kv_layer_floats * c->num_layers));
+  // The KV pool is sized by what a generate() call can actually touch (ctb_gpt_begin -> kv_reserve), not by
+  // max_batch x max_context: a handle that allows 32 rows x 4096 tokens costs nothing until such a call arrives.
+  h->kv = nullptr; h->kv_layer_floats = 0; h->kv_pages = 0;
   TRY(dalloc(&h->part, (size_t)c->max_batch * c->num_heads * h->nsplit_max * (c->head_dim + 2)));
   TRY(dalloc(&h->block_table, (size_t)c->max_batch * h->pages_per_row));
   TRY(dalloc(&h->seq_len, Bp));
@@ -290,10 +293,6 @@ extern "C" int ctb_gpt_create(const ctb_gpt_config* c, const float* weights_dev,
     h->flow_max_batch = getenv("CTB_FLOW_MAX_BATCH") ? std::max(0, std::min(FL_BMAX, atoi(getenv("CTB_FLOW_MAX_BATCH")))) : FL_BMAX;
   }
 #undef TRY
-  // static page assignment: row b owns pages [b*ppr, (b+1)*ppr); kernels only see the table
-  std::vector<int> bt_host((size_t)c->max_batch * h->pages_per_row);
-  for (size_t i = 0; i < bt_host.size(); ++i) bt_host[i] = (int)i;
-  cudaMemcpy(h->block_table, bt_host.data(), bt_host.size() * sizeof(int), cudaMemcpyHostToDevice);
   h->use_graph = getenv("CTB_NO_GRAPH") == nullptr;
   h->pf_enabled = getenv("CTB_NO_BATCHED_PREFILL") == nullptr;
   h->mega_ok = getenv("CTB_NO_MEGA") == nullptr && g_num_sms >= 128 && c->intermediate_size == 4 * KC &&
@@ -802,7 +801,8 @@ static int prefill_batched(ctb_gpt* h, cudaStream_t s) {
                                       nullptr, nullptr, 0, h->pf_qkv, nqkv))) return rc;
     k_prefill_rope_kv<<<dim3(T0, B), 256, 0, s>>>(pp);
     CTB_LAUNCH_CHECK();
-    k_prefill_attn<<<dim3(c.num_heads, B), 128, (size_t)T0 * sizeof(float), s>>>(pp);
+    k_prefill_attn<<<dim3((T0 + PF_ATT_WARPS - 1) / PF_ATT_WARPS, c.num_heads, B), PF_ATT_WARPS * 32,
+                     (size_t)PF_ATT_WARPS * T0 * sizeof(float), s>>>(pp);
     CTB_LAUNCH_CHECK();
     if ((rc = tc_gemm_launch<GE_SCALE_RES>(s, h->pf_attn, d, B, T0, d, d, 1, d, 1, 0, Whi + L.wo, Wlo + L.wo, h->pf_zeros,
                                            h->pf_ones, h->pf_resid, d, h->pf_resid, d))) return rc;
@@ -830,6 +830,37 @@ static int prefill_batched(ctb_gpt* h, cudaStream_t s) {
   return CTB_OK;
 }
 
+// Pages for B rows of up to `tokens` tokens each: grow the pool if needed (page = 16 tokens x K|V x heads x 64 floats per
+// layer) and assign row b the pages [b * need, (b + 1) * need) - kernels only ever see the block table.
+static int kv_reserve(ctb_gpt* h, int B, int tokens, cudaStream_t s) {
+  const ctb_gpt_config& c = h->cfg;
+  const size_t per_row = ((size_t)tokens + kPageTokens - 1) / kPageTokens;
+  const size_t need = per_row * (size_t)B;
+  const size_t page_floats = (size_t)2 * c.num_kv_heads * kPageTokens * c.head_dim;
+  if (need > h->kv_pages) {
+    CTB_CUDA(cudaStreamSynchronize(s));
+    if (h->kv) { cudaFree(h->kv); h->kv = nullptr; h->kv_pages = 0; }
+    const size_t pages = need + need / 8;  // a little head-room against re-allocation on slightly longer calls
+    if (cudaMalloc(reinterpret_cast<void**>(&h->kv), pages * page_floats * c.num_layers * sizeof(float)) != cudaSuccess) {
+      cudaGetLastError();
+      return set_err(CTB_ERR_NOMEM, "KV pool: %zu pages x %d layers (%.1f GB) do not fit", pages, c.num_layers,
+                     (double)(pages * page_floats * c.num_layers * 4) / 1e9);
+    }
+    CTB_CUDA(cudaMemsetAsync(h->kv, 0, pages * page_floats * c.num_layers * sizeof(float), s));
+    h->kv_pages = pages;
+    h->kv_layer_floats = pages * page_floats;
+    h->bt_B = 0;
+  }
+  if (h->bt_B == B && h->bt_per_row == per_row) return CTB_OK;  // table already describes this shape: nothing to upload
+  std::vector<int> bt((size_t)B * h->pages_per_row, 0);
+  for (int b = 0; b < B; ++b)
+    for (size_t i = 0; i < per_row; ++i) bt[(size_t)b * h->pages_per_row + i] = (int)((size_t)b * per_row + i);
+  CTB_CUDA(cudaMemcpyAsync(h->block_table, bt.data(), bt.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+  CTB_CUDA(cudaStreamSynchronize(s));  // bt is a host temporary
+  h->bt_B = B; h->bt_per_row = per_row;
+  return CTB_OK;
+}
+
 extern "C" int ctb_gpt_begin(ctb_gpt* h, int32_t B, int32_t T0, const float* emb_dev, const uint8_t* mask_dev,
                              const ctb_sampler_config* sampler, const float* q_noise_dev, int32_t max_new_token,
                              int32_t infer_text, int32_t* ids_out_dev, float* hiddens_out_dev, void* stream) {
@@ -845,6 +876,7 @@ extern "C" int ctb_gpt_begin(ctb_gpt* h, int32_t B, int32_t T0, const float* emb
   h->sampler = *sampler; h->q_noise = q_noise_dev; h->emb = emb_dev; h->mask = mask_dev;
   h->ids_out = ids_out_dev; h->hiddens_out = hiddens_out_dev;
   if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+  { int rc0 = kv_reserve(h, B, T0 + max_new_token, s); if (rc0) return rc0; }
   CTB_CUDA(cudaMemsetAsync(h->st, 0, sizeof(LoopState), s));
   CTB_CUDA(cudaMemsetAsync(h->seq_len, 0, sizeof(int) * h->bpad_max, s));
   CTB_CUDA(cudaMemsetAsync(h->finish, 0, h->bpad_max, s));

@@ -88,59 +88,53 @@ __global__ void k_prefill_rope_kv(const PrefillP p) {
   }
 }
 
-// causal attention over the row's valid prompt tokens; grid (Hq, B), 128 threads; hd == 64.
-// Query by query: scores by thread-per-key, block softmax, P.V by thread (dim, key half).
-__global__ void __launch_bounds__(128) k_prefill_attn(const PrefillP p) {
-  constexpr int HD = 64, NT = 128;
-  const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+// Causal attention over the row's valid prompt tokens, query-parallel: grid (ceil(T0 / 8), Hq, B), 8 warps per CTA,
+// ONE WARP PER QUERY (hd == 64).  Pass 1: lane-per-key scores into the warp's shared-memory row (same fma order per score
+// as the decode kernels), warp max; pass 2: exponentials + sum; pass 3: P.V with lane = two output dims, keys in order.
+// (Round 1 walked the queries of a (row, head) serially in one 128-thread CTA: 12 CTAs on 148 SMs and O(T^2) per CTA -
+// fine for 16-token prompts, hopeless for speaker-prompt prefixes of hundreds of tokens.)
+constexpr int PF_ATT_WARPS = 8;
+__global__ void __launch_bounds__(PF_ATT_WARPS * 32) k_prefill_attn(const PrefillP p) {
+  constexpr int HD = 64;
+  const int h = blockIdx.y, b = blockIdx.z, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n = p.nvalid[b];
+  const int t = blockIdx.x * PF_ATT_WARPS + warp;  // query position among the row's valid tokens
+  if (t >= n) return;                              // warp-uniform; the kernel has no block-wide barrier
+  extern __shared__ float pa_smem[];
+  float* s_p = pa_smem + (size_t)warp * p.T0;      // [T0] scores / probabilities of this warp's query
   const int hk = h / (p.Hq / p.Hkv);
   const int* bt = p.block_table + b * p.pages_per_row;
-  extern __shared__ float pa_smem[];
-  float* s_p = pa_smem;            // [n] scores / probabilities
-  __shared__ float s_q[HD], s_red[NT / 32], s_o[2][HD];
-  const int c0 = p.T0 - n;         // first valid column (left padding)
-  for (int t = 0; t < n; ++t) {    // query at position t attends keys 0..t
-    const size_t qrow = ((size_t)b * p.T0 + c0 + t) * p.Hq * HD + h * HD;
-    if (tid < HD) s_q[tid] = p.q[qrow + tid];
-    __syncthreads();
-    float m = -INFINITY;
-    for (int k = tid; k <= t; k += NT) {
-      const float4* kr = reinterpret_cast<const float4*>(p.kv + kv_off(bt[k / kPageTokens], 0, hk, k % kPageTokens, p.Hkv, HD));
-      float s = 0.f;
+  const int c0 = p.T0 - n;                         // first valid column (left padding)
+  const size_t qrow = ((size_t)b * p.T0 + c0 + t) * p.Hq * HD + h * HD;
+  float4 q[HD / 4];
 #pragma unroll
-      for (int i = 0; i < HD / 4; ++i) {
-        const float4 kk = kr[i];
-        s = fmaf(s_q[4 * i], kk.x, s); s = fmaf(s_q[4 * i + 1], kk.y, s);
-        s = fmaf(s_q[4 * i + 2], kk.z, s); s = fmaf(s_q[4 * i + 3], kk.w, s);
-      }
-      s *= p.scaling;
-      s_p[k] = s;
-      m = fmaxf(m, s);
+  for (int i = 0; i < HD / 4; ++i) q[i] = __ldg(reinterpret_cast<const float4*>(p.q + qrow) + i);
+  float m = -INFINITY;
+  for (int k = lane; k <= t; k += 32) {
+    const float4* kr = reinterpret_cast<const float4*>(p.kv + kv_off(bt[k / kPageTokens], 0, hk, k % kPageTokens, p.Hkv, HD));
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < HD / 4; ++i) {
+      const float4 kk = kr[i];
+      s = fmaf(q[i].x, kk.x, s); s = fmaf(q[i].y, kk.y, s); s = fmaf(q[i].z, kk.z, s); s = fmaf(q[i].w, kk.w, s);
     }
-    m = warp_max(m);
-    if ((tid & 31) == 0) s_red[tid >> 5] = m;
-    __syncthreads();
-    m = fmaxf(fmaxf(s_red[0], s_red[1]), fmaxf(s_red[2], s_red[3]));
-    __syncthreads();
-    float l = 0.f;
-    for (int k = tid; k <= t; k += NT) { const float e = expf(s_p[k] - m); s_p[k] = e; l += e; }
-    l = warp_sum(l);
-    if ((tid & 31) == 0) s_red[tid >> 5] = l;
-    __syncthreads();
-    l = (s_red[0] + s_red[1]) + (s_red[2] + s_red[3]);
-    const int d = tid & 63, half = tid >> 6;
-    float o = 0.f;
-    for (int k = half; k <= t; k += 2)
-      o = fmaf(s_p[k], p.kv[kv_off(bt[k / kPageTokens], 1, hk, k % kPageTokens, p.Hkv, HD) + d], o);
-    s_o[half][d] = o;
-    __syncthreads();
-    if (tid < HD) {
-      const int od = p.permute_qk ? tid : tid;  // V (and therefore the output) is never permuted
-      p.attn[qrow + od] = (s_o[0][tid] + s_o[1][tid]) / l;
-    }
-    __syncthreads();
+    s *= p.scaling;
+    s_p[k] = s;
+    m = fmaxf(m, s);
   }
+  m = warp_max(m);
+  float l = 0.f;
+  for (int k = lane; k <= t; k += 32) { const float e = expf(s_p[k] - m); s_p[k] = e; l += e; }
+  l = warp_sum(l);
+  __syncwarp();
+  float o0 = 0.f, o1 = 0.f;
+#pragma unroll 4
+  for (int k = 0; k <= t; ++k) {
+    const float2 v = *reinterpret_cast<const float2*>(p.kv + kv_off(bt[k / kPageTokens], 1, hk, k % kPageTokens, p.Hkv, HD) + 2 * lane);
+    const float pk = s_p[k];
+    o0 = fmaf(pk, v.x, o0); o1 = fmaf(pk, v.y, o1);
+  }
+  *reinterpret_cast<float2*>(p.attn + qrow + 2 * lane) = make_float2(o0 / l, o1 / l);  // V (and the output) is never permuted
 }
 
 // h = silu(gate) * up over [M, 2I] -> [M, I]

@@ -306,3 +306,51 @@ def decode_to_wavs(result_list: Sequence[torch.Tensor], use_decoder: bool, decod
             batch[i, :, : r.size(0)] = r.to(dev).permute(1, 0)
         wav = eng.tokens_to_wav(batch, 2)
     return wav.cpu().numpy()
+
+
+#: tokens of context each side of a decoded window: DVAE decoder +-75 mel frames (conv_in 2 x k3, 12 ConvNeXt k7
+#: dilation 2, out_conv k3), Vocos +-27 (embed k7, 8 ConvNeXt k7), iSTFT +-2 frames => +-104 frames = +-52 tokens
+STREAM_HALO_TOKENS = 56
+
+
+def _pad_batch(result_list: Sequence[torch.Tensor], use_decoder: bool, dev, t0: int, t1: int):
+    """Columns [t0, t1) of the zero-padded batch `decode_to_wavs` builds (quirk Q23 padding included)."""
+    n = len(result_list)
+    if use_decoder:
+        batch = torch.zeros(n, t1 - t0, result_list[0].size(1), dtype=torch.float32, device=dev)
+        for i, r in enumerate(result_list):
+            hi = min(int(r.size(0)), t1)
+            if hi > t0:
+                batch[i, : hi - t0] = r[t0:hi].to(dev)
+        return batch, 1
+    batch = torch.zeros(n, result_list[0].size(1), t1 - t0, dtype=torch.int32, device=dev)
+    for i, r in enumerate(result_list):
+        hi = min(int(r.size(0)), t1)
+        if hi > t0:
+            batch[i, :, : hi - t0] = r[t0:hi].to(dev).permute(1, 0)
+    return batch, 2
+
+
+@torch.inference_mode()
+def decode_to_wavs_window(result_list: Sequence[torch.Tensor], use_decoder: bool, decoder: DVAE, dvae: DVAE, a: int,
+                          b: int, halo: int = STREAM_HALO_TOKENS) -> np.ndarray:
+    """Samples [a, b) of ``decode_to_wavs(result_list, ...)`` without decoding the whole sequence.
+
+    Every layer of path 2 is local in time, so those samples depend only on the tokens within `halo` of the range: the
+    window [a // 512 - halo, ceil(b / 512) + halo] is decoded (clamped to the sequence, where the clamp reproduces the
+    true boundary) and the range is cut out of it.  This is SURVEY.md 8f N2: the reference re-decodes the cumulative
+    sequence at every streaming yield (core.py:455-503, O(n^2)); here a yield costs O(stream_batch + 2 halo) tokens."""
+    if len(result_list) == 0 or b <= a:
+        return np.zeros((len(result_list), 0), dtype=np.float32)
+    model = decoder if use_decoder else dvae
+    eng = model.engine
+    max_len = max(int(r.size(0)) for r in result_list)
+    total = 512 * max_len - 256
+    a, b = max(0, a), min(b, total)
+    t0 = max(0, a // 512 - halo)
+    t1 = min(max_len, (b + 511) // 512 + halo + 1)
+    if t1 - t0 < 2:  # a one-token window has a single frame pair: widen (the iSTFT needs >= 2 frames)
+        t0, t1 = max(0, t1 - 2), max(t1, min(max_len, t0 + 2))
+    batch, layout = _pad_batch(result_list, use_decoder, eng.device, t0, t1)
+    wav = eng.tokens_to_wav(batch, layout)
+    return wav[:, a - 512 * t0: b - 512 * t0].cpu().numpy()

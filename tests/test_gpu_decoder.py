@@ -181,3 +181,24 @@ def test_tensor_core_path_matches_fma_path():
     mel_tc = m["dec"].engine.dvae_decode(x, 1)
     assert (mel_tc - mel_fma).abs().max() < 2e-5 * max(1.0, float(mel_fma.abs().max()))
     assert rms(wav_tc, wav_fma) < 1e-5 * max(1e-3, float(wav_fma.pow(2).mean().sqrt())) + 1e-7
+
+
+@pytest.mark.parametrize("use_decoder", [True, False])
+def test_windowed_decode_equals_slices_of_the_full_decode(use_decoder):
+    """samples [a, b) decoded from the token window they depend on (halo 56 tokens each side) must be the
+    samples [a, b) of the full decode, for ranges at the start, in the middle, across the end and for ragged rows."""
+    from chattts_b200.decoder import decode_to_wavs, decode_to_wavs_window
+
+    m = models()
+    g = torch.Generator().manual_seed(13)
+    lens = [250, 101, 187]
+    res = [torch.randn(n, 768, generator=g) for n in lens] if use_decoder else \
+          [torch.randint(0, 625, (n, 4), generator=g) for n in lens]
+    full = decode_to_wavs([r.clone() for r in res], use_decoder, m["dec"], m["dv"])
+    total = full.shape[1]
+    assert total == 512 * 250 - 256
+    for a, b in ((0, 12000), (12000, 24000), (60000, 72000), (512 * 100 - 300, 512 * 102), (total - 5000, total), (0, total)):
+        win = decode_to_wavs_window([r.clone() for r in res], use_decoder, m["dec"], m["dv"], a, b)
+        assert win.shape == (3, b - a)
+        ref = full[:, a:b]
+        assert np.abs(win - ref).max() <= 1e-6 * max(1.0, float(np.abs(ref).max())) + 1e-9, (a, b, float(np.abs(win - ref).max()))

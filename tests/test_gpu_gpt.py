@@ -365,3 +365,20 @@ def test_multi_step_launch_matches_single_step_launches():
         assert torch.equal(outs["ink"].ids[b], outs["ext"].ids[b])
         assert torch.equal(outs["ink"].hiddens[b], outs["ext"].hiddens[b])
     assert len(outs["ink"].ids[0]) < 200  # high temperature: this row stops at an EOS well before max_new_token
+
+
+def test_batched_prefill_512_token_prompts():
+    """VERDICT r1 #8 / SURVEY.md 8f N1: prompts as long as speaker-prompt prefixes (up to 512 tokens, ragged) through the
+    query-parallel prefill attention; first tokens and hidden states against the CPU oracle."""
+    from gpu_util import build_gpt
+
+    gpt, embed, gs, es = build_gpt(max_batch=4, max_context=640)
+    orc = GPTOracle(gs, es)
+    lengths = [512, 300, 40]
+    ids, mask, tmask = synth_prompt_batch(lengths, seed=29)
+    ref = orc.generate(orc.embed_prompt(ids, tmask), ids, torch.tensor([0.3] * 4), 625, attention_mask=mask,
+                       max_new_token=12, min_new_token=12, sampler=SamplerParams(), return_hidden=True, manual_seed=5)
+    out = _run(gpt, embed, lengths, 29, 5, 12)[-1]
+    for b in range(3):
+        assert torch.equal(out.ids[b].cpu(), ref.ids[b]), b
+        assert (out.hiddens[b].cpu() - ref.hiddens[b]).abs().max() < 2e-4
