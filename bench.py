@@ -262,7 +262,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     if world == 1 and not args.no_sweep:
         del gpt
         torch.cuda.empty_cache()
-        for bb in (8, 32):
+        for bb in (2, 4, 8, 32):
             g2 = GPT(cfg.gpt, embed, device=dev, device_gpt=dev, max_batch=bb, max_context=PROMPT_LEN + tokens + 16)
             g2.load_state(synth_gpt_state(0))
             i2, m2, tm2, _, sc2, q2 = build_inputs(bb, tokens, seed=1)

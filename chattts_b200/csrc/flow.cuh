@@ -85,6 +85,7 @@ struct FlowP {
   unsigned long long* arena;  // FL_ARENA_WORDS, zeroed at create
   unsigned* epoch;            // tag base of the next launch (advanced by CTA 0 at the end of every launch)
   int R;                      // replicas in use (1..FL_RMAX)
+  int l2_ahead;               // 1: prefetch every weight task one layer ahead into L2 (CTB_FLOW_L2_AHEAD)
   unsigned long long* trace;  // optional globaltimer stamps of CTA 0 (1 + 5 * L + 1)
   // ---- multi-step mode (decode, audio): the sampling tail and the finish bookkeeping run inside the kernel
   int nsteps;                 // decode steps this launch runs (1 when ink == 0)
@@ -263,6 +264,17 @@ __device__ __forceinline__ bool fl_issue(const FlowP& p, const FlowGeo* gs, cons
 #pragma unroll
       for (int k = 0; k < 4; ++k)
         if (k < ncopy) fl_bulk(dst + k * bytes, src + (int64_t)k * e.y, (uint32_t)bytes, bar, kind ? pol_kv : pol_w);
+      if (p.l2_ahead && kind == 0) {
+        // Two-level stream: the SAME task of the next layer (of layer 0 of the next step after the last one) is pulled
+        // HBM -> L2 now, so that its shared-memory copy, posted a layer later, is an L2 hit.  A global load issued after
+        // a bulk copy only returns after it: a copy that completes in ~0.3 us instead of a DRAM latency holds the polls
+        // behind it that much less.  One layer of weights (37.75 MB) fits the 126 MB L2 next to the exchange arena.
+        const float* nsrc = it.l + 1 < p.L ? src + p.layer_stride : src - (int64_t)(p.L - 1) * p.layer_stride;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (k < ncopy)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nsrc + (int64_t)k * e.y), "r"((uint32_t)bytes) : "memory");
+      }
     }
     if (++it.k == it.ntab) { it.k = 0; it.l++; }
     it.n++;

@@ -82,6 +82,7 @@ struct ctb_gpt {
   unsigned long long* trace;  // CTB_MEGA_TRACE=1: per-phase timestamps of the last step
   bool flow_ok;      // dataflow decode step (flow.cuh), B <= 4: default back end for those batches
   int flow_R;        // replicas of the broadcast exchange regions (CTB_FLOW_R)
+  int flow_l2_ahead;  // weight tasks prefetched one layer ahead into L2 (CTB_FLOW_L2_AHEAD)
   int flow_max_batch; // batches that use it (CTB_FLOW_MAX_BATCH, default 4)
   unsigned long long* flow_arena;
   unsigned* flow_epoch;
@@ -290,6 +291,7 @@ extern "C" int ctb_gpt_create(const ctb_gpt_config* c, const float* weights_dev,
     // measured on B200 (tools/flow_check.py): one copy of the exchange words is fastest (replicas multiply the 8-byte
     // stores; the read hot-spot they were meant to relieve is the smaller effect), and the kernel beats k_step at every batch it is built for (B <= 4)
     h->flow_R = getenv("CTB_FLOW_R") ? std::max(1, std::min(FL_RMAX, atoi(getenv("CTB_FLOW_R")))) : 1;
+    h->flow_l2_ahead = getenv("CTB_FLOW_L2_AHEAD") ? atoi(getenv("CTB_FLOW_L2_AHEAD")) : 0;
     h->flow_max_batch = getenv("CTB_FLOW_MAX_BATCH") ? std::max(0, std::min(FL_BMAX, atoi(getenv("CTB_FLOW_MAX_BATCH")))) : FL_BMAX;
   }
 #undef TRY
@@ -637,6 +639,7 @@ static int launch_step_flow(ctb_gpt* h, int col, bool sample, cudaStream_t s, in
   m.hidden_out = h->hiddens_out; m.hidden_stride = h->max_new * c.hidden_size;
   m.rows_per_item = h->infer_text ? 1 : c.num_vq; m.V = h->infer_text ? c.num_text_tokens : c.num_audio_tokens;
   m.arena = h->flow_arena; m.epoch = h->flow_epoch; m.R = h->flow_R; m.trace = h->trace;
+  m.l2_ahead = h->flow_l2_ahead;
   m.ink = nsteps > 0 ? 1 : 0; m.nsteps = nsteps > 0 ? nsteps : 1; m.samp = h->sampler; m.q_noise = h->q_noise;
   m.finish = h->finish; m.end_idx = h->end_idx; m.ids_w = h->ids_out;
   switch (bt_for(h->B)) {

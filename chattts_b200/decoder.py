@@ -205,6 +205,20 @@ class TokenDecoder:
         return self.vocos_decode(None)
 
 
+def _decode_coef(coef) -> torch.Tensor:
+    """``DVAE(coef=...)`` of the reference takes a base16384 string of 100 float32 (dvae.py:220-226)."""
+    if coef is None:
+        return torch.rand(100)
+    if isinstance(coef, str):
+        try:
+            import pybase16384 as b14  # the reference's own dependency; not bundled here
+        except ImportError as e:
+            raise _lib.CtbError("a base16384 `coef` string needs the pybase16384 package (the reference's dependency); "
+                                "pass a tensor of 100 floats instead") from e
+        return torch.from_numpy(np.frombuffer(b14.decode_from_string(coef), dtype=np.float32).copy())
+    return torch.as_tensor(coef, dtype=torch.float32).reshape(-1)
+
+
 class DVAE:
     """Drop-in for the reference ``DVAE`` decode branch (dvae.py:209-297): ``dvae(inp)`` /
     ``dvae(inp, mode="decode")`` -> mel [B, 100, 2T].  ``mode="encode"`` (speaker enrolment,
@@ -235,8 +249,11 @@ class DVAE:
 
     def load_state_dict(self, state: State):
         self.state = {k: v.detach().float() for k, v in state.items()}
-        if self.coef is not None:
-            self.state["coef"] = torch.as_tensor(self.coef, dtype=torch.float32).reshape(1, -1, 1)
+        # dvae.py:220-226: the constructor's `coef` (a base16384 string in the reference, a tensor here as well) only
+        # initialises the persistent buffer; a checkpoint that carries `coef` overrides it in load_state_dict, and a
+        # model with neither gets torch.rand(100)
+        if "coef" not in self.state:
+            self.state["coef"] = _decode_coef(self.coef).reshape(1, -1, 1)
         blob = pack_dvae(self.state, self.stack, self.dim, self.vq)
         vb = pack_vocos(self.vocos.state, self.vocos.cfg) if self.vocos is not None else None
         self.engine = TokenDecoder(self.stack, self.dim, self.vq, self.vocos.cfg if self.vocos else VocosConfig(),

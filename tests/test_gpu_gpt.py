@@ -382,3 +382,19 @@ def test_batched_prefill_512_token_prompts():
     for b in range(3):
         assert torch.equal(out.ids[b].cpu(), ref.ids[b]), b
         assert (out.hiddens[b].cpu() - ref.hiddens[b]).abs().max() < 2e-4
+
+
+def test_kv_pool_and_handle_are_reused_across_calls_of_different_shapes():
+    """The KV pool is sized per generate() call (kv_reserve): a short call, then a much longer / wider one, then the
+    short one again on the SAME handle must all reproduce the oracle (pages re-assigned, pool grown once)."""
+    from gpu_util import build_gpt
+
+    gpt, embed, gs, es = build_gpt(max_batch=4, max_context=1280)
+    orc = GPTOracle(gs, es)
+    for lengths, steps in (([9], 12), ([33, 120, 7], 200), ([9], 12)):
+        ids, mask, tmask = synth_prompt_batch(lengths, seed=71)
+        ref = orc.generate(orc.embed_prompt(ids, tmask), ids, torch.tensor([0.3] * 4), 625, attention_mask=mask,
+                           max_new_token=steps, min_new_token=steps, sampler=SamplerParams(), return_hidden=True, manual_seed=9)
+        out = _run(gpt, embed, lengths, 71, 9, steps)[-1]
+        for b in range(len(lengths)):
+            assert torch.equal(out.ids[b].cpu(), ref.ids[b]), (lengths, b)

@@ -111,14 +111,15 @@ def main():
 
     print(f"old k_step  B=1: {time_steps(ref, embed, 1, a.tokens):8.1f} us/step", flush=True)
     for R in [int(x) for x in a.sweep.split(",")]:
-        g, _ = make({"CTB_FLOW_R": str(R), "CTB_FLOW_MAX_BATCH": "4"})
-        t = {B: time_steps(g, embed, B, a.tokens) for B in (1, 2, 4)}
-        print(f"flow R={R:2d}: " + "  ".join(f"B={B}: {t[B]:7.1f} us/step" for B in t), flush=True)
-        del g
-        torch.cuda.empty_cache()
+        for l2a in (0, 1):
+            g, _ = make({"CTB_FLOW_R": str(R), "CTB_FLOW_MAX_BATCH": "4", "CTB_FLOW_L2_AHEAD": str(l2a)})
+            t = {B: time_steps(g, embed, B, a.tokens) for B in (1, 2, 4)}
+            print(f"flow R={R:2d} l2_ahead={l2a}: " + "  ".join(f"B={B}: {t[B]:7.1f} us/step" for B in t), flush=True)
+            del g
+            torch.cuda.empty_cache()
 
     # per-phase trace of CTA 0 (last step)
-    tr, _ = make({"CTB_MEGA_TRACE": "1", "CTB_FLOW_R": "1"})
+    tr, _ = make({"CTB_MEGA_TRACE": "1", "CTB_FLOW_R": "1", "CTB_FLOW_L2_AHEAD": os.environ.get("TRACE_L2_AHEAD", "1")})
     time_steps(tr, embed, 1, 64, reps=1)
     buf = (C.c_ulonglong * 256)()
     _lib.check(lib.ctb_gpt_debug_trace(tr._handle, buf, 256))
