@@ -22,25 +22,15 @@ from .config import Config
 from .decoder import decode_to_wavs_window, DVAE, Vocos, decode_to_wavs
 from .embed import Embed
 from .gpt import GPT
+from .norm import Normalizer
 from .processors import gen_logits
-
-
-class _IdentityNormalizer:
-    def __call__(self, text, do_text_normalization=True, do_homophone_replacement=True, lang=None):
-        return text
-
-    def register(self, name, normalizer):
-        return True
-
-    def destroy(self):
-        pass
 
 
 class Chat:
     def __init__(self, logger=logging.getLogger(__name__)):
         self.logger = logger
         self.config = Config()
-        self.normalizer = _IdentityNormalizer()
+        self.normalizer = Normalizer(logger=logger)        # no homophone map until load() finds the asset (core.py:39-42)
         self.context = GPT.Context()
 
     # core.py:49-64
@@ -57,14 +47,14 @@ class Chat:
              device: Optional[torch.device] = None, coef: Optional[torch.Tensor] = None, use_flash_attn=False,
              use_vllm=False, experimental: bool = False) -> bool:
         """core.py:137-163.  ``compile`` / ``use_flash_attn`` / ``use_vllm`` / ``experimental`` are accepted and
-        ignored (one back end).  Asset discovery, tokenizer, normaliser and speaker come
+        ignored (one back end).  Asset discovery, tokenizer, the homophone map and speaker come
         from the reference package, which must be importable; weights go through the reference's own loaders
         (safetensors + ``LlamaModel.from_pretrained``)."""
         try:
             import ChatTTS as ref  # the reference package (out-of-scope host components)
         except Exception as e:  # pragma: no cover - needs the reference + assets
-            raise RuntimeError("Chat.load() needs the reference `ChatTTS` package for asset download, tokenizer, "
-                               "normaliser and speaker handling; use Chat.load_states() for in-memory weights") from e
+            raise RuntimeError("Chat.load() needs the reference `ChatTTS` package for asset download, tokenizer "
+                               "and speaker handling; use Chat.load_states() for in-memory weights") from e
         from dataclasses import asdict
 
         helper = ref.Chat(self.logger)
@@ -84,7 +74,8 @@ class Chat:
         from ChatTTS.model import Speaker, Tokenizer
 
         dev = device or torch.device("cuda")
-        self.normalizer = helper.normalizer
+        homophones = os.path.join(os.path.dirname(ref.__file__), "res", "homophones_map.json")   # core.py:39-42
+        self.normalizer = Normalizer(homophones if os.path.exists(homophones) else None, self.logger)
         return self.load_states(states, tokenizer=Tokenizer(paths["tokenizer_path"]),
                                 speaker=Speaker(self.config.gpt.hidden_size, helper.config.spk_stat, dev), device=dev,
                                 coef=coef)
