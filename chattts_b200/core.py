@@ -115,7 +115,10 @@ class Chat:
         return self.speaker.sample_random()
 
     def sample_audio_speaker(self, wav) -> str:
-        raise NotImplementedError("DVAE encode branch (speaker enrolment) is outside the hot path (SURVEY.md 8f N3)")
+        """core.py:179-180: wav (24 kHz, 1-D) -> DVAE codes -> speaker-prompt string for ``InferCodeParams.spk_smp``."""
+        if self.dvae.audio_encoder is None:
+            raise RuntimeError("this DVAE checkpoint carries no encoder / VQ weights: cannot sample a speaker from audio")
+        return self.speaker.encode_prompt(self.dvae.sample_audio(wav))
 
     # ------------------------------------------------------------------ params (core.py:182-206)
     @dataclass(repr=False, eq=False)
@@ -196,10 +199,15 @@ class Chat:
                 yield text
                 return
         if split_text and len(text) > 1 and params_infer_code.spk_smp is None:
-            # core.py:435-453 samples a speaker from sentence 0 via the DVAE *encode* branch (out of the hot
-            # path): not rebuilt - pass spk_smp / spk_emb explicitly or split_text=False.
-            self.logger.warning("auto speaker sampling from the first sentence is not available; "
-                                "sentences are generated without a sampled speaker prompt")
+            # core.py:435-453: sentence 0 is synthesised once on its own and its audio, re-encoded by the DVAE encode
+            # branch, becomes the speaker prompt (spk_smp / txt_smp) of every sentence - this keeps one voice across them
+            refer_text = text[0]
+            result = next(self._infer_code(refer_text, False, self.device, use_decoder, params_infer_code))
+            wavs = self._decode_to_wavs(result.hiddens if use_decoder else result.ids, use_decoder)
+            result.destroy()
+            assert len(wavs) == 1
+            params_infer_code.spk_smp = self.sample_audio_speaker(wavs[0])
+            params_infer_code.txt_smp = refer_text
         if stream:
             length, pass_batch_count = 0, 0
         if split_text:

@@ -247,7 +247,7 @@ static int dvae_run(ctb_decoder* h, const void* in, int layout, int B, int T, fl
     GfsqP g{};
     g.ids = static_cast<const int32_t*>(in); g.out = h->staged_in; g.B = B; g.T = T; g.G = c.vq_groups;
     g.R = c.vq_residual; g.levels = c.vq_levels & 0xff; g.nlev = 4; g.per_group = c.vq_dim / c.vq_groups;
-    g.scale_base = (float)((c.vq_levels >> 8) ? (c.vq_levels >> 8) : (g.levels - 1));
+    g.scale_base = (float)(((c.vq_levels >> 8) & 0xff) ? ((c.vq_levels >> 8) & 0xff) : (g.levels - 1));
     g.w = W + L.vq_w; g.b = W + L.vq_b;
     k_gfsq_dequant<<<B * T * c.vq_groups, 128, 0, s>>>(g);
     CTB_LAUNCH_CHECK();
@@ -325,4 +325,164 @@ extern "C" int ctb_vocos_decode(ctb_decoder* h, const float* mel_dev, int32_t B,
     return set_err(CTB_ERR_STATE, "no mel of this shape was left in the handle by ctb_dvae_decode");
   { int rc = dec_reserve(h, (size_t)B * F, (cudaStream_t)stream); if (rc) return rc; }
   return vocos_run(h, mel_dev, B, F, wav_dev, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------ DVAE encode branch (speaker enrolment)
+// DVAE.forward(mode="encode") (dvae.py:265-274): wav -> log-mel / coef -> downsample_conv -> encoder stack -> GFSQ indices.
+namespace {
+
+constexpr int ENC_NFFT = 1024, ENC_HOP = 256, ENC_NBIN = ENC_NFFT / 2 + 1, ENC_SPEC = 1056;  // MelSpectrogramFeatures defaults (dvae.py:176-181)
+
+struct EncOff {
+  int64_t dft_w, fb, coef, ds0_w, ds0_b, ds1_w, ds1_b, in0_w, in0_b, in2_w, in2_b, conv_out_w, vq_w, vq_b, total;
+  BlockOff blk[64];
+};
+
+// Blob order of the encode branch; chattts_b200/decoder.py::pack_dvae_encoder writes the same sequence.
+EncOff enc_layout(const ctb_convstack_config& c) {
+  EncOff o{};
+  int64_t off = 0;
+  o.dft_w = take(off, (int64_t)ENC_SPEC * ENC_NFFT);          // [1056 (re_k, im_k interleaved + zero rows), 1024] windowed forward DFT
+  o.fb = take(off, (int64_t)ENC_NBIN * MEL_PAD);              // [513][128] mel filterbank, bin-major
+  o.coef = take(off, MEL_PAD);
+  o.ds0_w = take(off, (int64_t)c.idim * 3 * MEL_PAD);         // Conv1d(100 -> dim, k3, p1), mel channels padded to 128
+  o.ds0_b = take(off, c.idim);
+  o.ds1_w = take(off, (int64_t)c.idim * 3 * 2 * c.idim);      // Conv1d(dim -> dim, k4, s2, p1) over frame PAIRS: 3 taps x 2*dim
+  o.ds1_b = take(off, c.idim);
+  o.in0_w = take(off, (int64_t)c.bn_dim * 3 * c.idim);
+  o.in0_b = take(off, c.bn_dim);
+  o.in2_w = take(off, (int64_t)c.hidden * 3 * c.bn_dim);
+  o.in2_b = take(off, c.hidden);
+  for (int i = 0; i < c.n_layer; ++i) block_layout(o.blk[i], off, c.hidden, 4 * c.hidden);
+  o.conv_out_w = take(off, (int64_t)c.odim * c.hidden);
+  const int nlev = 4;
+  o.vq_w = take(off, (int64_t)c.vq_groups * nlev * (c.vq_dim / c.vq_groups));  // project_in [G][4][dim/G]
+  o.vq_b = take(off, (int64_t)c.vq_groups * nlev);
+  o.total = off;
+  return o;
+}
+
+}  // namespace
+
+struct ctb_encoder {
+  ctb_convstack_config c;
+  EncOff L;
+  const float* W;
+  float *W_hi, *W_lo;
+  bool use_tc;
+  int64_t max_samples;
+  int max_frames;
+  float *padded, *spec, *mel_tm, *bufX, *bufY, *bufA, *bufB, *bufH;
+};
+
+extern "C" int64_t ctb_dvae_encoder_blob_floats(const ctb_convstack_config* c) { return c ? enc_layout(*c).total : -1; }
+
+extern "C" int ctb_dvae_encoder_destroy(ctb_encoder* h) {
+  if (!h) return CTB_OK;
+  void* ptrs[] = {h->W_hi, h->W_lo, h->padded, h->spec, h->mel_tm, h->bufX, h->bufY, h->bufA, h->bufB, h->bufH};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  delete h;
+  return CTB_OK;
+}
+
+extern "C" int ctb_dvae_encoder_create(const ctb_convstack_config* c, const float* blob_dev, int64_t max_samples,
+                                       ctb_encoder** out) {
+  if (!c || !blob_dev || !out) return set_err(CTB_ERR_ARG, "null argument");
+  if (c->kernel != 7 || c->n_layer > 64 || c->idim % 32 || c->bn_dim % 16 || c->hidden % 128 || c->hidden > 512 || c->odim % 16)
+    return set_err(CTB_ERR_ARG, "unsupported encoder stack");
+  if (c->vq_dim != c->odim || c->vq_groups < 1 || c->vq_dim % c->vq_groups || c->vq_residual < 1 || (c->vq_levels & 0xff) < 2)
+    return set_err(CTB_ERR_ARG, "the encoder's odim must equal vq_dim (GFSQ input)");
+  if (max_samples <= ENC_NFFT / 2 || max_samples > (int64_t)1 << 28) return set_err(CTB_ERR_ARG, "max_samples out of range");
+  int ndev = 0;
+  CTB_CUDA(cudaGetDeviceCount(&ndev));
+  if (ndev < 1) return set_err(CTB_ERR_CUDA, "no CUDA device: chattts_b200 has no CPU path");
+  ctb_encoder* h = new ctb_encoder();
+  memset(h, 0, sizeof(*h));
+  h->c = *c; h->L = enc_layout(*c); h->W = blob_dev; h->max_samples = max_samples;
+  h->max_frames = (int)(max_samples / ENC_HOP) + 1;
+  h->use_tc = getenv("CTB_DECODER_FMA") == nullptr;
+  const size_t F = h->max_frames, FP = (F + 1) / 2;
+  cudaError_t e = cudaSuccess;
+  auto A = [&](float** p, size_t n) { if (e == cudaSuccess) e = cudaMalloc((void**)p, n * sizeof(float)); };
+  A(&h->padded, (F + 3) * ENC_HOP);
+  A(&h->spec, (F + 3) * ENC_SPEC);
+  A(&h->mel_tm, F * MEL_PAD);
+  A(&h->bufX, 2 * FP * c->idim);
+  A(&h->bufY, FP * c->idim);
+  A(&h->bufA, FP * std::max(c->hidden, c->bn_dim));
+  A(&h->bufB, FP * std::max(std::max(c->hidden, c->bn_dim), c->odim));
+  A(&h->bufH, FP * 4 * c->hidden);
+  if (h->use_tc) { A(&h->W_hi, h->L.total); A(&h->W_lo, h->L.total); }
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    ctb_dvae_encoder_destroy(h);
+    return set_err(CTB_ERR_NOMEM, "encoder buffers: %s", cudaGetErrorString(e));
+  }
+  if (h->use_tc) {
+    k_split_tf32<<<1024, 256>>>(h->W, h->W_hi, h->W_lo, h->L.total);
+    CTB_CUDA(cudaDeviceSynchronize());
+  }
+  *out = h;
+  return CTB_OK;
+}
+
+extern "C" int ctb_dvae_encode(ctb_encoder* h, const float* wav_dev, int64_t n_samples, int32_t* ids_dev,
+                               int32_t ids_capacity_tokens, int32_t* n_tokens_out, float* mel_dev, float* margin_dev,
+                               void* stream) {
+  if (!h || !wav_dev || !ids_dev || !n_tokens_out) return set_err(CTB_ERR_ARG, "null argument");
+  if (n_samples <= ENC_NFFT / 2) return set_err(CTB_ERR_ARG, "reflect padding needs more than %d samples", ENC_NFFT / 2);
+  if (n_samples > h->max_samples) return set_err(CTB_ERR_ARG, "%lld samples exceed this handle (max_samples=%lld)",
+                                                 (long long)n_samples, (long long)h->max_samples);
+  const ctb_convstack_config& c = h->c;
+  const EncOff& L = h->L;
+  const float* W = h->W;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int F = (int)(n_samples / ENC_HOP) + 1;     // torch.stft(center=True)
+  const int T = F / 2;                              // Conv1d(k4, s2, p1): floor((F + 2 - 4) / 2) + 1
+  *n_tokens_out = T;
+  if (T < 1) return set_err(CTB_ERR_ARG, "audio too short for one token");
+  if (T > ids_capacity_tokens) return set_err(CTB_ERR_ARG, "ids buffer holds %d tokens, %d needed", ids_capacity_tokens, T);
+  const GemmCtx gc{h->W, h->W_hi, h->W_lo, h->use_tc};
+  int rc;
+  // framing + windowed DFT as one GEMM: rows of `hop` samples, a frame = 4 consecutive rows (taps)
+  const int NC = F + 3;
+  const int64_t total = (int64_t)NC * ENC_HOP;
+  k_reflect_pad<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(wav_dev, h->padded, n_samples, total, ENC_NFFT / 2);
+  CTB_LAUNCH_CHECK();
+  if ((rc = gemm<GE_NONE>(s, gc, h->padded, ENC_HOP, NC, ENC_SPEC, ENC_NFFT, ENC_NFFT / ENC_HOP, ENC_HOP, 1, 0, NC, W + L.dft_w,
+                          nullptr, nullptr, nullptr, 0, h->spec, ENC_SPEC))) return rc;
+  k_mel_log<MEL_PAD><<<F, MEL_PAD, ENC_NBIN * sizeof(float), s>>>(h->spec, ENC_SPEC, ENC_NBIN, W + L.fb, W + L.coef, MEL, h->mel_tm);
+  CTB_LAUNCH_CHECK();
+  if (mel_dev) {
+    dim3 g((F + 31) / 32, (MEL + 31) / 32, 1);
+    k_tm_to_cf<<<g, dim3(32, 8), 0, s>>>(h->mel_tm, mel_dev, 1, MEL, F, MEL_PAD);
+    CTB_LAUNCH_CHECK();
+  }
+  // downsample_conv (dvae.py:231-236): Conv1d(100 -> dim, k3, p1) + GELU; Conv1d(dim -> dim, k4, s2, p1) + GELU.
+  // The stride-2 conv runs over frame pairs [F/2 rows, 2*dim]: out[t] = W0 x[2t-1] + W1 x[2t] + W2 x[2t+1] + W3 x[2t+2]
+  // = 3 taps over pair rows with the weights re-packed (zeros where a pair half is not touched).
+  const int FP = (F + 1) / 2;
+  if (F & 1) CTB_CUDA(cudaMemsetAsync(h->bufX + (size_t)F * c.idim, 0, (size_t)c.idim * sizeof(float), s));
+  if ((rc = gemm<GE_GELU>(s, gc, h->mel_tm, MEL_PAD, F, c.idim, 3 * MEL_PAD, 3, MEL_PAD, 1, 1, F, W + L.ds0_w, W + L.ds0_b,
+                          nullptr, nullptr, 0, h->bufX, c.idim))) return rc;
+  if ((rc = gemm<GE_GELU>(s, gc, h->bufX, 2 * c.idim, FP, c.idim, 3 * 2 * c.idim, 3, 2 * c.idim, 1, 1, FP, W + L.ds1_w,
+                          W + L.ds1_b, nullptr, nullptr, 0, h->bufY, c.idim))) return rc;
+  // encoder = DVAEDecoder(idim -> odim) over the first T rows (dvae.py:131-172)
+  if ((rc = gemm<GE_GELU>(s, gc, h->bufY, c.idim, T, c.bn_dim, 3 * c.idim, 3, c.idim, 1, 1, T, W + L.in0_w, W + L.in0_b,
+                          nullptr, nullptr, 0, h->bufB, c.bn_dim))) return rc;
+  if ((rc = gemm<GE_BIAS>(s, gc, h->bufB, c.bn_dim, T, c.hidden, 3 * c.bn_dim, 3, c.bn_dim, 1, 1, T, W + L.in2_w, W + L.in2_b,
+                          nullptr, nullptr, 0, h->bufA, c.hidden))) return rc;
+  for (int i = 0; i < c.n_layer; ++i)
+    if ((rc = convnext(s, gc, W, L.blk[i], h->bufA, h->bufB, h->bufH, T, T, c.hidden, 4 * c.hidden, c.dilation))) return rc;
+  if ((rc = gemm<GE_NONE>(s, gc, h->bufA, c.hidden, T, c.odim, c.hidden, 1, c.hidden, 1, 0, T, W + L.conv_out_w, nullptr,
+                          nullptr, nullptr, 0, h->bufB, c.odim))) return rc;
+  FsqQuantP q{};
+  q.x = h->bufB; q.ids = ids_dev; q.margin = margin_dev; q.T = T; q.G = c.vq_groups; q.R = c.vq_residual;
+  q.levels = c.vq_levels & 0xff; q.nlev = 4; q.per_group = c.vq_dim / c.vq_groups;
+  q.scale_base = (float)(((c.vq_levels >> 8) & 0xff) ? ((c.vq_levels >> 8) & 0xff) : (q.levels - 1));
+  q.bound_input = ((c.vq_levels >> 16) & 1) ? 0 : 1;
+  q.w = W + L.vq_w; q.b = W + L.vq_b;
+  k_fsq_quant<<<T * c.vq_groups, 128, 0, s>>>(q);
+  CTB_LAUNCH_CHECK();
+  return CTB_OK;
 }

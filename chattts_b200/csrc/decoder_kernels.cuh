@@ -323,6 +323,96 @@ __global__ void k_overlap_add(const float* __restrict__ frames, const float* __r
   wav[i] = s / env;
 }
 
+// ---------------------------------------------------------------- DVAE encode branch (dvae.py:175-206,265-274,102-128)
+// torch.stft(center=True, pad_mode="reflect") framing: padded[i] = wav[reflect(i - n_fft/2)], written as rows of
+// `hop` samples so that frame f = rows f .. f + n_fft/hop - 1 (a "conv" with n_fft/hop taps for the GEMM gather).
+__global__ void k_reflect_pad(const float* __restrict__ wav, float* __restrict__ out, int64_t L, int64_t total, int half) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int64_t j = i - half;
+  if (j < 0) j = -j;
+  if (j >= L) j = 2 * (L - 1) - j;
+  out[i] = (j >= 0 && j < L) ? wav[j] : 0.f;   // rows past the last frame are never read as a full window
+}
+
+// |STFT| (power = 1) -> mel filterbank -> log(clip(., 1e-5)) / coef  (dvae.py:199-206,267-268), one frame per block.
+// spec [rows, ldspec] interleaved (re_k, im_k); fb [nbin][MELP] (bin-major, mel padded with zero columns);
+// out time-major [F, MELP] with the pad channels written as 0.
+template <int MELP>
+__global__ void __launch_bounds__(MELP) k_mel_log(const float* __restrict__ spec, int ldspec, int nbin,
+                                                   const float* __restrict__ fb, const float* __restrict__ coef, int n_mels,
+                                                   float* __restrict__ out) {
+  extern __shared__ float s_mag[];
+  const float* row = spec + (size_t)blockIdx.x * ldspec;
+  for (int k = threadIdx.x; k < nbin; k += MELP) {
+    const float re = row[2 * k], im = row[2 * k + 1];
+    s_mag[k] = sqrtf(fmaf(re, re, im * im));
+  }
+  __syncthreads();
+  const int m = threadIdx.x;
+  float a = 0.f;
+  for (int k = 0; k < nbin; ++k) a = fmaf(s_mag[k], fb[(size_t)k * MELP + m], a);
+  out[(size_t)blockIdx.x * MELP + m] = m < n_mels ? logf(fmaxf(a, 1e-5f)) / coef[m] : 0.f;
+}
+
+// GFSQ.forward (dvae.py:102-128) -> GroupedResidualFSQ [3p]: per (frame, group) project_in Linear(dim/G -> nlev), then
+// R residual FSQ stages: q = round(bound(res / s_r)), code = q / (levels / 2), res -= code * s_r, s_r = base^-r;
+// index_r = sum_k (q_k + levels / 2) * levels^k.  x time-major [T, G * per_group]; ids [G * R, T] (c = g * R + r).
+struct FsqQuantP {
+  const float* x; int32_t* ids; float* margin;  // margin (optional) [G * R, T]: distance of the closest bound() to a rounding edge
+  int T, G, R, levels, nlev, per_group;
+  float scale_base; int bound_input;
+  const float* w;   // [G][nlev][per_group]
+  const float* b;   // [G][nlev]
+};
+__device__ __forceinline__ float fsq_bound(float z, int levels) {
+  const float half_l = (float)(levels - 1) * (1.0f + 1e-3f) * 0.5f;
+  const float offset = (levels & 1) ? 0.0f : 0.5f;
+  const float shift = atanhf(offset / half_l);
+  return tanhf(z + shift) * half_l - offset;
+}
+__global__ void __launch_bounds__(128) k_fsq_quant(const FsqQuantP p) {
+  const int t = blockIdx.x / p.G, g = blockIdx.x % p.G;
+  const float* x = p.x + ((size_t)t * p.G + g) * p.per_group;
+  __shared__ float s_part[4][8];
+  float acc[8];
+  for (int k = 0; k < p.nlev; ++k) acc[k] = 0.f;
+  for (int c = threadIdx.x; c < p.per_group; c += 128) {
+    const float xv = x[c];
+    for (int k = 0; k < p.nlev; ++k) acc[k] = fmaf(xv, p.w[((size_t)g * p.nlev + k) * p.per_group + c], acc[k]);
+  }
+  for (int k = 0; k < p.nlev; ++k) {
+    float v = acc[k];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  float res[8];
+  for (int k = 0; k < p.nlev; ++k) {
+    const float z = ((s_part[0][k] + s_part[1][k]) + (s_part[2][k] + s_part[3][k])) + p.b[g * p.nlev + k];
+    res[k] = p.bound_input ? fsq_bound(z, p.levels) : z;
+  }
+  const float half_w = (float)(p.levels / 2);
+  float sc = 1.f;
+  for (int r = 0; r < p.R; ++r) {
+    int idx = 0, mul = 1;
+    float mg = 1.f;
+    for (int k = 0; k < p.nlev; ++k) {
+      const float bz = fsq_bound(res[k] / sc, p.levels);
+      const float q = rintf(bz);                       // torch.round: half to even
+      mg = fminf(mg, 0.5f - fabsf(bz - q));
+      res[k] -= (q / half_w) * sc;
+      idx += ((int)q + p.levels / 2) * mul;
+      mul *= p.levels;
+    }
+    p.ids[((size_t)g * p.R + r) * p.T + t] = idx;
+    if (p.margin) p.margin[((size_t)g * p.R + r) * p.T + t] = mg;
+    sc /= p.scale_base;
+  }
+}
+
 #endif  // CTB_DECODER_KERNELS_IMPL
 
 }  // namespace ctb

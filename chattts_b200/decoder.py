@@ -205,24 +205,136 @@ class TokenDecoder:
         return self.vocos_decode(None)
 
 
+
+# ---------------------------------------------------------------------------------------------------------------------
+# DVAE encode branch (speaker enrolment; SURVEY.md 8f N3): wav -> codes.  dvae.py:175-206,231-236,265-274,102-128.
+ENC_NFFT, ENC_HOP, ENC_SPEC_K, ENC_SR = 1024, 256, 1056, 24000   # MelSpectrogramFeatures defaults (dvae.py:176-181)
+
+
+def mel_filterbank(n_freqs: int = ENC_NFFT // 2 + 1, n_mels: int = MEL, sample_rate: int = ENC_SR) -> torch.Tensor:
+    """[3p] torchaudio ``melscale_fbanks(n_freqs, 0, sr/2, n_mels, sr, norm=None, mel_scale="htk")`` -> [n_freqs, n_mels]:
+    triangles between HTK-mel-equidistant points (what ``torchaudio.transforms.MelSpectrogram`` builds, dvae.py:188-195)."""
+    all_freqs = torch.linspace(0, sample_rate // 2, n_freqs)
+    m_max = 2595.0 * math.log10(1.0 + (sample_rate / 2.0) / 700.0)
+    m_pts = torch.linspace(0.0, m_max, n_mels + 2)
+    f_pts = 700.0 * (10.0 ** (m_pts / 2595.0) - 1.0)
+    f_diff = f_pts[1:] - f_pts[:-1]
+    slopes = f_pts.unsqueeze(0) - all_freqs.unsqueeze(1)
+    down = (-1.0 * slopes[:, :-2]) / f_diff[:-1]
+    up = slopes[:, 2:] / f_diff[1:]
+    return torch.clamp(torch.min(down, up), min=0.0)
+
+
+def dft_basis(n_fft: int = ENC_NFFT, spec_k: int = ENC_SPEC_K, window: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Windowed forward real DFT as GEMM weights [spec_k, n_fft]: row 2k = hann[n] cos(2 pi k n / N), row 2k+1 =
+    -hann[n] sin(2 pi k n / N) (periodic Hann, ``torch.stft`` / torchaudio ``Spectrogram`` defaults); zero pad rows."""
+    n = torch.arange(n_fft, dtype=torch.float64)[None, :]
+    k = torch.arange(n_fft // 2 + 1, dtype=torch.float64)[:, None]
+    ang = 2 * math.pi * ((n * k) % n_fft) / n_fft
+    w = (torch.hann_window(n_fft, periodic=True, dtype=torch.float64) if window is None else window.double().cpu())[None, :]
+    basis = torch.zeros(spec_k, n_fft, dtype=torch.float64)
+    basis[0: 2 * (n_fft // 2 + 1): 2] = torch.cos(ang) * w
+    basis[1: 2 * (n_fft // 2 + 1): 2] = -torch.sin(ang) * w
+    return basis.float()
+
+
+def pack_dvae_encoder(s: State, stack: ConvStackConfig, dim: int, vq: VQConfig) -> torch.Tensor:
+    """Blob of ``ctb_dvae_encoder_create`` (order of decoder_api.cu::enc_layout)."""
+    assert stack.idim == dim and stack.odim == vq.dim, "encoder stack must map DVAE dim -> vq dim"
+    pk = _Packer()
+    # a real checkpoint carries torchaudio's buffers (window, filterbank); the synthetic states do not
+    pk.add(dft_basis(window=s.get("preprocessor_mel.mel_spec.spectrogram.window")))
+    fb = s.get("preprocessor_mel.mel_spec.mel_scale.fb")
+    fb = mel_filterbank() if fb is None else fb.detach().float().cpu()
+    pk.add(torch.cat([fb, torch.zeros(fb.shape[0], MEL_PAD - MEL)], 1))
+    pk.add(torch.cat([s["coef"].reshape(-1), torch.ones(MEL_PAD - MEL)]))
+    pk.add(_tap_major(s["downsample_conv.0.weight"], MEL_PAD))
+    pk.add(s["downsample_conv.0.bias"])
+    w = s["downsample_conv.2.weight"]                       # [dim, dim, 4], stride 2, padding 1
+    z = torch.zeros(dim, dim)
+    # out[t] = W0 x[2t-1] + W1 x[2t] + W2 x[2t+1] + W3 x[2t+2] over pair rows r_t = (x[2t] | x[2t+1])
+    pairs = torch.stack([torch.cat([z, w[:, :, 0]], 1), torch.cat([w[:, :, 1], w[:, :, 2]], 1),
+                         torch.cat([w[:, :, 3], z], 1)], dim=1)   # [dim, 3 taps, 2*dim]
+    pk.add(pairs.reshape(dim, -1))
+    pk.add(s["downsample_conv.2.bias"])
+    pk.add(_tap_major(s["encoder.conv_in.0.weight"]))
+    pk.add(s["encoder.conv_in.0.bias"])
+    pk.add(_tap_major(s["encoder.conv_in.2.weight"]))
+    pk.add(s["encoder.conv_in.2.bias"])
+    for i in range(stack.n_layer):
+        _pack_block(pk, s, f"encoder.decoder_block.{i}.", "weight")
+    pk.add(s["encoder.conv_out.weight"][:, :, 0])
+    pk.add(torch.stack([s[f"vq_layer.quantizer.rvqs.{g}.project_in.weight"] for g in range(vq.G)]))
+    pk.add(torch.stack([s[f"vq_layer.quantizer.rvqs.{g}.project_in.bias"] for g in range(vq.G)]))
+    return pk.blob()
+
+
+class AudioEncoder:
+    """One ``ctb_encoder`` handle: ``DVAE.forward(mode="encode")`` on the GPU (wav [L] -> ids [G*R, T])."""
+
+    def __init__(self, stack: ConvStackConfig, dim: int, vq: VQConfig, blob: torch.Tensor, device,
+                 max_samples: int = 30 * ENC_SR, fsq_scale_base: int = 4, fsq_bound_input: bool = True):
+        _lib.require_cuda()
+        lib = _lib.load()
+        self.device = torch.device(device)
+        self.vq, self.max_samples = vq, max_samples
+        self._cfg = _stack_cfg(stack, dim, vq, fsq_scale_base)
+        if not fsq_bound_input:
+            self._cfg.vq_levels |= 1 << 16
+        assert blob.numel() == lib.ctb_dvae_encoder_blob_floats(C.byref(self._cfg)), "encoder blob layout mismatch"
+        self._blob = blob.to(self.device, torch.float32).contiguous()
+        self._handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(lib.ctb_dvae_encoder_create(C.byref(self._cfg), C.c_void_p(self._blob.data_ptr()), max_samples,
+                                                   C.byref(self._handle)))
+
+    def __del__(self):
+        try:
+            if self._handle:
+                _lib.load().ctb_dvae_encoder_destroy(self._handle)
+        except Exception:
+            pass
+
+    def encode(self, wav: torch.Tensor, want_mel: bool = False, want_margin: bool = False):
+        lib = _lib.load()
+        wav = wav.to(self.device, torch.float32).contiguous().view(-1)
+        n = wav.numel()
+        frames = n // ENC_HOP + 1
+        cap = max(frames // 2, 1)
+        rows = self.vq.G * self.vq.R
+        ids = torch.empty(rows, cap, dtype=torch.int32, device=self.device)
+        mel = torch.empty(MEL, frames, dtype=torch.float32, device=self.device) if want_mel else None
+        margin = torch.empty(rows, cap, dtype=torch.float32, device=self.device) if want_margin else None
+        n_tok = C.c_int32(0)
+        with torch.cuda.device(self.device):
+            _lib.check(lib.ctb_dvae_encode(self._handle, C.c_void_p(wav.data_ptr()), n, C.c_void_p(ids.data_ptr()), cap,
+                                           C.byref(n_tok), C.c_void_p(mel.data_ptr()) if want_mel else None,
+                                           C.c_void_p(margin.data_ptr()) if want_margin else None,
+                                           C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        assert n_tok.value == cap
+        out = (ids,)
+        if want_mel:
+            out += (mel,)
+        if want_margin:
+            out += (margin,)
+        return out if len(out) > 1 else ids
+
+
 def _decode_coef(coef) -> torch.Tensor:
     """``DVAE(coef=...)`` of the reference takes a base16384 string of 100 float32 (dvae.py:220-226)."""
     if coef is None:
         return torch.rand(100)
     if isinstance(coef, str):
-        try:
-            import pybase16384 as b14  # the reference's own dependency; not bundled here
-        except ImportError as e:
-            raise _lib.CtbError("a base16384 `coef` string needs the pybase16384 package (the reference's dependency); "
-                                "pass a tensor of 100 floats instead") from e
+        from . import b14
+
         return torch.from_numpy(np.frombuffer(b14.decode_from_string(coef), dtype=np.float32).copy())
     return torch.as_tensor(coef, dtype=torch.float32).reshape(-1)
 
 
 class DVAE:
-    """Drop-in for the reference ``DVAE`` decode branch (dvae.py:209-297): ``dvae(inp)`` /
-    ``dvae(inp, mode="decode")`` -> mel [B, 100, 2T].  ``mode="encode"`` (speaker enrolment,
-    dvae.py:265-274) is outside the hot path and raises."""
+    """Drop-in for the reference ``DVAE`` (dvae.py:209-303): ``dvae(inp)`` / ``dvae(inp, mode="decode")`` -> mel
+    [B, 100, 2T]; ``dvae(wav, mode="encode")`` -> ids [1, G*R, T] and ``sample_audio(wav)`` -> [G*R, T] (speaker
+    enrolment, dvae.py:265-274,299-303) when the model was built with an ``encoder_config`` and a ``vq_config``."""
 
     def __init__(self, decoder_config: Union[dict, ConvStackConfig], encoder_config=None,
                  vq_config: Union[dict, VQConfig, None] = None, dim: int = 512, coef: Optional[torch.Tensor] = None,
@@ -233,6 +345,11 @@ class DVAE:
                                                 if k in ConvStackConfig.__dataclass_fields__})
         if isinstance(vq_config, dict):
             vq_config = VQConfig(**vq_config)
+        if isinstance(encoder_config, dict):
+            encoder_config = ConvStackConfig(**{k: v for k, v in encoder_config.items()
+                                                if k in ConvStackConfig.__dataclass_fields__})
+        self.enc_stack: Optional[ConvStackConfig] = encoder_config
+        self.audio_encoder: Optional[AudioEncoder] = None
         self.stack, self.vq, self.dim = decoder_config, vq_config, dim
         self.device = torch.device(device)
         self.coef = coef
@@ -258,18 +375,38 @@ class DVAE:
         vb = pack_vocos(self.vocos.state, self.vocos.cfg) if self.vocos is not None else None
         self.engine = TokenDecoder(self.stack, self.dim, self.vq, self.vocos.cfg if self.vocos else VocosConfig(),
                                    blob, vb, self.device, self.max_batch, self.max_tokens)
+        self.audio_encoder = None
+        if self.enc_stack is not None and self.vq is not None and "encoder.conv_in.0.weight" in self.state:
+            self.audio_encoder = AudioEncoder(self.enc_stack, self.dim, self.vq,
+                                              pack_dvae_encoder(self.state, self.enc_stack, self.dim, self.vq), self.device,
+                                              max_samples=max(512 * self.max_tokens, 30 * ENC_SR))
         return self
 
     def eval(self):
         return self
 
+    def __repr__(self) -> str:
+        """dvae.py:250-253: the base16384 form of ``coef``."""
+        from . import b14
+
+        return b14.encode_to_string(self.state["coef"].cpu().numpy().astype(np.float32).tobytes())
+
     @torch.inference_mode()
     def __call__(self, inp: torch.Tensor, mode: str = "decode") -> torch.Tensor:
-        if mode != "decode":
-            raise NotImplementedError("DVAE encode branch is outside the B200 hot path (SURVEY.md 8f N3)")
         if self.engine is None:
             raise _lib.CtbError("DVAE weights not loaded")
+        # dvae.py:265: the encode branch is taken only when the model has an encoder AND a VQ layer; anything else
+        # falls through to decode, like the reference
+        if mode == "encode" and self.audio_encoder is not None:
+            return self.audio_encoder.encode(inp).unsqueeze(0)
         return self.engine.dvae_decode(inp, 2 if self.vq is not None else 0)
+
+    @torch.inference_mode()
+    def sample_audio(self, wav: Union[np.ndarray, torch.Tensor]) -> torch.Tensor:
+        """dvae.py:299-303: wav [L] -> codes [G*R, T]."""
+        if isinstance(wav, np.ndarray):
+            wav = torch.from_numpy(wav)
+        return self(wav, "encode").squeeze_(0)
 
 
 class Vocos:

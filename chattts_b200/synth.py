@@ -9,6 +9,7 @@ independent of global RNG state and identical on every box.
 """
 from __future__ import annotations
 
+import math
 from typing import Dict
 
 import torch
@@ -101,7 +102,8 @@ def _convnext(g, s, p, dim, inter, scale_name, scale_val):
     s[p + scale_name] = scale_val * (1.0 + _normal(g, (dim,), 0.1))
 
 
-def synth_dvae_state(seed: int, stack: ConvStackConfig, dim: int, vq: VQConfig | None = None) -> State:
+def synth_dvae_state(seed: int, stack: ConvStackConfig, dim: int, vq: VQConfig | None = None,
+                     encoder: ConvStackConfig | None = None) -> State:
     """``DVAE.state_dict()`` decode-side keys (reference dvae.py:131-172,209-243).
 
     ``stack`` = decoder stack config, ``dim`` = ``DVAE(dim=...)`` (out_conv input channels).
@@ -122,6 +124,19 @@ def synth_dvae_state(seed: int, stack: ConvStackConfig, dim: int, vq: VQConfig |
             # GroupedResidualFSQ -> rvqs.{g}.project_out : Linear(len(levels) -> dim/G)
             _linear(g, s, f"vq_layer.quantizer.rvqs.{grp}.project_in", len(vq.levels), per_group)
             _linear(g, s, f"vq_layer.quantizer.rvqs.{grp}.project_out", per_group, len(vq.levels))
+    if encoder is not None:
+        # encode-branch keys (dvae.py:229-236), drawn AFTER everything above so that the decode-side values (and the
+        # committed fixtures made from them) do not move
+        _conv(g, s, "downsample_conv.0", dim, 100, 3)
+        _conv(g, s, "downsample_conv.2", dim, dim, 4)
+        _conv(g, s, "encoder.conv_in.0", encoder.bn_dim, encoder.idim, 3)
+        _conv(g, s, "encoder.conv_in.2", encoder.hidden, encoder.bn_dim, 3)
+        for i in range(encoder.n_layer):
+            _convnext(g, s, f"encoder.decoder_block.{i}.", encoder.hidden, encoder.hidden * 4, "weight", 0.25)
+        _conv(g, s, "encoder.conv_out", encoder.odim, encoder.hidden, 1, bias=False)
+        if vq is not None:
+            for grp in range(vq.G):   # spread the projected values over several FSQ levels (bound() saturates beyond ~2)
+                s[f"vq_layer.quantizer.rvqs.{grp}.project_in.weight"] *= 32.0
     return s
 
 
@@ -148,6 +163,30 @@ def synth_all(seed: int = 0, std: float = 0.02, cfg: Config = Config()) -> Dict[
         "gpt": synth_gpt_state(seed, std, cfg.gpt),
         "embed": synth_embed_state(seed + 1, cfg.gpt),
         "decoder": synth_dvae_state(seed + 2, cfg.decoder, cfg.decoder.idim),
-        "dvae": synth_dvae_state(seed + 3, cfg.dvae.decoder, cfg.dvae.decoder.idim, cfg.dvae.vq),
+        "dvae": synth_dvae_state(seed + 3, cfg.dvae.decoder, cfg.dvae.decoder.idim, cfg.dvae.vq, encoder=cfg.dvae.encoder),
         "vocos": synth_vocos_state(seed + 4, cfg.vocos),
     }
+
+
+def synth_speech_like(seconds: float = 2.0, seed: int = 0, sample_rate: int = 24000) -> torch.Tensor:
+    """A waveform with speech-like variety for the encode-branch tests: 80 ms segments that are silent, voiced (harmonic
+    stack with a moving pitch) or noisy, under a slow amplitude envelope, so that the log-mel moves over its whole range."""
+    g = _gen(seed)
+    n = int(seconds * sample_rate)
+    seg = int(0.08 * sample_rate)
+    t = torch.arange(n, dtype=torch.float32) / sample_rate
+    out = torch.zeros(n)
+    kinds = torch.randint(0, 4, ((n + seg - 1) // seg,), generator=g)
+    pitch = 90.0 + 160.0 * torch.rand(kinds.numel(), generator=g)
+    for i, k in enumerate(kinds.tolist()):
+        sl = slice(i * seg, min(n, (i + 1) * seg))
+        if k == 0:
+            continue
+        if k in (1, 2):
+            f0 = float(pitch[i])
+            for h in range(1, 9 if k == 1 else 4):
+                out[sl] += torch.sin(2 * math.pi * f0 * h * t[sl]) / h
+        else:
+            out[sl] += torch.randn(t[sl].numel(), generator=g) * 0.5
+    env = 0.15 + 0.35 * (1 + torch.sin(2 * math.pi * 1.7 * t)) / 2
+    return (out * env * 0.5).clamp_(-1.0, 1.0)

@@ -26,7 +26,7 @@ extern "C" {
 #define CTB_ERR_STATE (-3)
 #define CTB_ERR_NOMEM (-4)
 
-#define CTB_ABI_VERSION 2
+#define CTB_ABI_VERSION 3
 
 /* ---- library ------------------------------------------------------------------- */
 int ctb_abi_version(void);
@@ -168,7 +168,8 @@ typedef struct ctb_convstack_config {
   int32_t idim, odim, hidden, n_layer, bn_dim, kernel, dilation; /* dvae.py:131-172 */
   int32_t out_dim;    /* DVAE(dim=...) : out_conv input channels; 100 mel bins out (dvae.py:236) */
   int32_t vq_dim, vq_groups, vq_residual; /* GFSQ (dvae.py:69-97); vq_dim = 0: no VQ layer */
-  int32_t vq_levels;  /* low byte: levels per dim (5); bits 8..: residual scale base (0 => levels-1) */
+  int32_t vq_levels;  /* low byte: levels per dim (5); bits 8..15: residual scale base (0 => levels-1);
+                       * bit 16 (encode only): 1 = do NOT bound() the projected input before the first residual stage */
 } ctb_convstack_config;
 
 typedef struct ctb_vocos_config {
@@ -199,6 +200,27 @@ int ctb_dvae_decode(ctb_decoder* h, const void* in_dev, int32_t in_layout, int32
 /* Vocos.decode (core.py:505-510): mel [B,100,F] channels-first (NULL: the mel left in the handle by
  * the last ctb_dvae_decode) -> wav [B, hop*(F-1)] fp32 */
 int ctb_vocos_decode(ctb_decoder* h, const float* mel_dev, int32_t B, int32_t F, float* wav_dev, void* stream);
+
+/* ---- waveform -> codes: replaces DVAE.forward(mode="encode") (ChatTTS/model/dvae.py:265-274), i.e. ------
+ * MelSpectrogramFeatures (dvae.py:175-206; n_fft 1024, hop 256, 100 mel bins, center/reflect, power 1, log(clip 1e-5))
+ * -> / coef -> downsample_conv (dvae.py:231-236) -> encoder DVAEDecoder stack (dvae.py:131-172) -> GFSQ.forward indices
+ * (dvae.py:102-128).  Caller: Chat.sample_audio_speaker (core.py:179-180) and the automatic speaker sample of
+ * multi-sentence infer() (core.py:435-453).
+ * cfg: idim = DVAE dim (512), odim = vq_dim (1024), hidden / n_layer / bn_dim / kernel / dilation of the encoder stack,
+ * vq_* as for the decoder.  The blob holds the windowed DFT basis, the mel filterbank, coef, the two downsample convs,
+ * the stack and the FSQ project_in matrices (order: chattts_b200/decoder.py::pack_dvae_encoder). */
+typedef struct ctb_encoder ctb_encoder;
+int64_t ctb_dvae_encoder_blob_floats(const ctb_convstack_config* enc_cfg);
+int ctb_dvae_encoder_create(const ctb_convstack_config* enc_cfg, const float* blob_dev, int64_t max_samples,
+                            ctb_encoder** out);
+int ctb_dvae_encoder_destroy(ctb_encoder* h);
+/* wav_dev [n_samples] fp32 (24 kHz) -> ids_dev [G*R, T] int32 with T = (n_samples / 256 + 1) / 2 written to the HOST
+ * int *n_tokens_out; ids_capacity_tokens = tokens ids_dev (and margin_dev) can hold per code row.
+ * mel_dev (optional) [100, n_samples / 256 + 1]: the log-mel BEFORE the division by coef is not kept; this is mel / coef.
+ * margin_dev (optional) [G*R, T] fp32: distance of the closest pre-rounding value to a rounding edge (0 .. 0.5), the
+ * decision margin the parity tests use to tell a real mismatch from fp32 reordering noise. */
+int ctb_dvae_encode(ctb_encoder* h, const float* wav_dev, int64_t n_samples, int32_t* ids_dev,
+                    int32_t ids_capacity_tokens, int32_t* n_tokens_out, float* mel_dev, float* margin_dev, void* stream);
 
 #ifdef __cplusplus
 }

@@ -95,9 +95,33 @@ def gen_dvae():
     print("dvae", mel.shape, float(mel.abs().mean()))
 
 
+def gen_dvae_encode():
+    """Encode branch: mel and encoder output from the REFERENCE's modules (torchaudio mel, downsample convs, encoder
+    stack); ids / margins from the oracle's FSQ restatement applied to the reference's encoder output (third-party
+    quantiser absent - parity unpinned for that last step)."""
+    from chattts_b200.synth import synth_speech_like
+    from oracle.dvae_oracle import fsq_quantize
+    from oracle.ref_models import build_reference_dvae_encoder
+
+    cfg = Config()
+    st = synth_dvae_state(3, cfg.dvae.decoder, cfg.dvae.decoder.idim, cfg.dvae.vq, encoder=cfg.dvae.encoder)
+    ref = build_reference_dvae_encoder(st, cfg.dvae.decoder, cfg.dvae.encoder, cfg.dvae.decoder.idim)
+    seconds, seed = 1.37, 7                      # 32 880 samples: not a multiple of the hop, odd frame count
+    wav = synth_speech_like(seconds, seed)
+    with torch.inference_mode():
+        mel = ref.preprocessor_mel(wav.clone())
+        mel = mel / ref.coef.view(100, 1)
+        x = ref.encoder(ref.downsample_conv(mel).unsqueeze(0))
+    ids, margin = fsq_quantize(x.transpose(1, 2).clone(), st)
+    np.savez_compressed(os.path.join(OUT, "dvae_encode.npz"), seconds=seconds, seed=seed, mel_over_coef=mel.numpy(),
+                        ids=ids.numpy().astype(np.int32), margin=margin.numpy())
+    print("dvae encode", tuple(ids.shape), "frames", mel.shape[1], "min margin", float(margin.min()))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
     gen_gpt()
     gen_sampler()
     gen_dvae()
+    gen_dvae_encode()

@@ -58,3 +58,16 @@ def build_reference_dvae(state, stack_cfg, dim):
     own = {k: v for k, v in state.items() if not k.startswith("vq_layer")}
     m.load_state_dict(own)
     return m
+
+
+def build_reference_dvae_encoder(state, dec_cfg, enc_cfg, dim):
+    """Reference ``DVAE`` with the encode-side modules (dvae.py:229-236) but no ``vq_layer`` (vector_quantize_pytorch is
+    absent): exposes ``preprocessor_mel``, ``downsample_conv`` and ``encoder`` for piecewise pinning."""
+    load_reference()
+    from ChatTTS.model import DVAE
+
+    d = lambda c: dict(idim=c.idim, odim=c.odim, hidden=c.hidden, n_layer=c.n_layer, bn_dim=c.bn_dim)
+    m = DVAE(decoder_config=d(dec_cfg), encoder_config=d(enc_cfg), dim=dim).eval()
+    missing = m.load_state_dict({k: v for k, v in state.items() if not k.startswith("vq_layer")}, strict=False)
+    assert not missing.unexpected_keys and all(k.startswith("preprocessor_mel.") for k in missing.missing_keys), missing
+    return m

@@ -13,7 +13,7 @@ def test_library_builds_and_loads():
     path = build.build()
     assert os.path.exists(path)
     lib = _lib.load()
-    assert lib.ctb_abi_version() == 2
+    assert lib.ctb_abi_version() == 3
 
 
 def test_every_declared_symbol_is_exported():

@@ -73,3 +73,28 @@ def test_dvae_decoder_branch_matches_reference():
     got = dvae_decode(x, st)
     assert want.shape == got.shape == (2, 100, 40)
     assert (want - got).abs().max() < 1e-5 * max(1.0, float(want.abs().max()))
+
+
+def test_dvae_encode_branch_matches_reference_up_to_the_quantizer():
+    """Encode branch (dvae.py:265-274) piece by piece against the reference's own modules: MelSpectrogramFeatures
+    (torchaudio), downsample_conv, encoder stack.  The FSQ quantiser itself is third-party and absent (parity unpinned)."""
+    from chattts_b200.config import Config
+    from chattts_b200.synth import synth_dvae_state, synth_speech_like
+    from oracle.dvae_oracle import dvae_encode, mel_features
+    from oracle.ref_models import build_reference_dvae_encoder
+
+    cfg = Config()
+    st = synth_dvae_state(3, cfg.dvae.decoder, cfg.dvae.decoder.idim, cfg.dvae.vq, encoder=cfg.dvae.encoder)
+    ref = build_reference_dvae_encoder(st, cfg.dvae.decoder, cfg.dvae.encoder, cfg.dvae.decoder.idim)
+    for seconds, seed in ((1.3, 0), (2.0, 1)):
+        wav = synth_speech_like(seconds, seed)
+        with torch.inference_mode():
+            mel_ref = ref.preprocessor_mel(wav.clone())
+            x_ref = ref.encoder(ref.downsample_conv(mel_ref / ref.coef.view(100, 1)).unsqueeze(0))
+        mel = mel_features(wav)
+        assert mel.shape == mel_ref.shape == (100, wav.numel() // 256 + 1)
+        assert (mel - mel_ref).abs().max() < 2e-4          # same stft; the filterbank matmul runs in another order
+        ids, margin, _, x = dvae_encode(wav, st, return_parts=True)
+        assert x.shape == x_ref.shape == (1, 1024, (wav.numel() // 256 + 1) // 2)
+        assert (x - x_ref).abs().max() < 1e-4 * max(1.0, float(x_ref.abs().max()))
+        assert ids.shape == (1, 4, x.shape[2]) and int(ids.min()) >= 0 and int(ids.max()) < 625
