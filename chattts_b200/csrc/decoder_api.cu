@@ -331,10 +331,10 @@ extern "C" int ctb_vocos_decode(ctb_decoder* h, const float* mel_dev, int32_t B,
 // DVAE.forward(mode="encode") (dvae.py:265-274): wav -> log-mel / coef -> downsample_conv -> encoder stack -> GFSQ indices.
 namespace {
 
-constexpr int ENC_NFFT = 1024, ENC_HOP = 256, ENC_NBIN = ENC_NFFT / 2 + 1, ENC_SPEC = 1056;  // MelSpectrogramFeatures defaults (dvae.py:176-181)
+constexpr int ENC_NFFT = 1024, ENC_HOP = 256, ENC_NBIN = ENC_NFFT / 2 + 1, ENC_LDMAG = 516;  // MelSpectrogramFeatures defaults (dvae.py:176-181)
 
 struct EncOff {
-  int64_t dft_w, fb, coef, ds0_w, ds0_b, ds1_w, ds1_b, in0_w, in0_b, in2_w, in2_b, conv_out_w, vq_w, vq_b, total;
+  int64_t window, fb, coef, ds0_w, ds0_b, ds1_w, ds1_b, in0_w, in0_b, in2_w, in2_b, conv_out_w, vq_w, vq_b, total;
   BlockOff blk[64];
 };
 
@@ -342,7 +342,7 @@ struct EncOff {
 EncOff enc_layout(const ctb_convstack_config& c) {
   EncOff o{};
   int64_t off = 0;
-  o.dft_w = take(off, (int64_t)ENC_SPEC * ENC_NFFT);          // [1056 (re_k, im_k interleaved + zero rows), 1024] windowed forward DFT
+  o.window = take(off, ENC_NFFT);                             // analysis window (periodic Hann, fp32 like torch.hann_window)
   o.fb = take(off, (int64_t)ENC_NBIN * MEL_PAD);              // [513][128] mel filterbank, bin-major
   o.coef = take(off, MEL_PAD);
   o.ds0_w = take(off, (int64_t)c.idim * 3 * MEL_PAD);         // Conv1d(100 -> dim, k3, p1), mel channels padded to 128
@@ -405,7 +405,7 @@ extern "C" int ctb_dvae_encoder_create(const ctb_convstack_config* c, const floa
   cudaError_t e = cudaSuccess;
   auto A = [&](float** p, size_t n) { if (e == cudaSuccess) e = cudaMalloc((void**)p, n * sizeof(float)); };
   A(&h->padded, (F + 3) * ENC_HOP);
-  A(&h->spec, (F + 3) * ENC_SPEC);
+  A(&h->spec, F * ENC_LDMAG);
   A(&h->mel_tm, F * MEL_PAD);
   A(&h->bufX, 2 * FP * c->idim);
   A(&h->bufY, FP * c->idim);
@@ -444,14 +444,13 @@ extern "C" int ctb_dvae_encode(ctb_encoder* h, const float* wav_dev, int64_t n_s
   if (T > ids_capacity_tokens) return set_err(CTB_ERR_ARG, "ids buffer holds %d tokens, %d needed", ids_capacity_tokens, T);
   const GemmCtx gc{h->W, h->W_hi, h->W_lo, h->use_tc};
   int rc;
-  // framing + windowed DFT as one GEMM: rows of `hop` samples, a frame = 4 consecutive rows (taps)
-  const int NC = F + 3;
-  const int64_t total = (int64_t)NC * ENC_HOP;
+  // framing (reflect padding) -> |STFT| as a double-precision direct DFT -> mel filterbank, log, / coef
+  const int64_t total = (int64_t)(F + 3) * ENC_HOP;
   k_reflect_pad<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(wav_dev, h->padded, n_samples, total, ENC_NFFT / 2);
   CTB_LAUNCH_CHECK();
-  if ((rc = gemm<GE_NONE>(s, gc, h->padded, ENC_HOP, NC, ENC_SPEC, ENC_NFFT, ENC_NFFT / ENC_HOP, ENC_HOP, 1, 0, NC, W + L.dft_w,
-                          nullptr, nullptr, nullptr, 0, h->spec, ENC_SPEC))) return rc;
-  k_mel_log<MEL_PAD><<<F, MEL_PAD, ENC_NBIN * sizeof(float), s>>>(h->spec, ENC_SPEC, ENC_NBIN, W + L.fb, W + L.coef, MEL, h->mel_tm);
+  k_stft_mag<ENC_NFFT><<<dim3(F, (ENC_NBIN + 255) / 256), 256, 0, s>>>(h->padded, W + L.window, ENC_HOP, ENC_NBIN, h->spec, ENC_LDMAG);
+  CTB_LAUNCH_CHECK();
+  k_mel_log<MEL_PAD><<<F, MEL_PAD, ENC_NBIN * sizeof(float), s>>>(h->spec, ENC_LDMAG, ENC_NBIN, W + L.fb, W + L.coef, MEL, h->mel_tm);
   CTB_LAUNCH_CHECK();
   if (mel_dev) {
     dim3 g((F + 31) / 32, (MEL + 31) / 32, 1);

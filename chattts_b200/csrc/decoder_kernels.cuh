@@ -324,8 +324,7 @@ __global__ void k_overlap_add(const float* __restrict__ frames, const float* __r
 }
 
 // ---------------------------------------------------------------- DVAE encode branch (dvae.py:175-206,265-274,102-128)
-// torch.stft(center=True, pad_mode="reflect") framing: padded[i] = wav[reflect(i - n_fft/2)], written as rows of
-// `hop` samples so that frame f = rows f .. f + n_fft/hop - 1 (a "conv" with n_fft/hop taps for the GEMM gather).
+// torch.stft(center=True, pad_mode="reflect") framing: padded[i] = wav[reflect(i - n_fft/2)]; frame f = padded[f*hop .. +n_fft).
 __global__ void k_reflect_pad(const float* __restrict__ wav, float* __restrict__ out, int64_t L, int64_t total, int half) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -335,19 +334,44 @@ __global__ void k_reflect_pad(const float* __restrict__ wav, float* __restrict__
   out[i] = (j >= 0 && j < L) ? wav[j] : 0.f;   // rows past the last frame are never read as a full window
 }
 
-// |STFT| (power = 1) -> mel filterbank -> log(clip(., 1e-5)) / coef  (dvae.py:199-206,267-268), one frame per block.
-// spec [rows, ldspec] interleaved (re_k, im_k); fb [nbin][MELP] (bin-major, mel padded with zero columns);
-// out time-major [F, MELP] with the pad channels written as 0.
+// |STFT| (power = 1) of one frame per block row, evaluated as a direct DFT in DOUBLE precision: thread = frequency bin,
+// x[n] * hann[n] (exact in double) times an exact-index twiddle table cos/sin(2 pi ((k n) mod N) / N).  The reference runs
+// an fp32 FFT (torch.stft); a direct fp32 DFT would carry ~10x its rounding error, and the log that follows amplifies any
+// error in the bins far below the frame's peak into the codes.  In double the result is the correctly rounded magnitude,
+// i.e. at least as close to the exact value as the reference's own output.  Cost: 1 M DFMA per frame - negligible.
+template <int NFFT>
+__global__ void __launch_bounds__(256) k_stft_mag(const float* __restrict__ padded, const float* __restrict__ window, int hop,
+                                                   int nbin, float* __restrict__ mag, int ldmag) {
+  __shared__ double s_c[NFFT], s_s[NFFT], s_x[NFFT];
+  const float* x = padded + (size_t)blockIdx.x * hop;
+  for (int j = threadIdx.x; j < NFFT; j += 256) {
+    double sn, cs;
+    sincospi(2.0 * (double)j / (double)NFFT, &sn, &cs);
+    s_c[j] = cs; s_s[j] = sn;
+    s_x[j] = (double)x[j] * (double)window[j];
+  }
+  __syncthreads();
+  const int k = blockIdx.y * 256 + threadIdx.x;
+  if (k >= nbin) return;
+  double re = 0.0, im = 0.0;
+#pragma unroll 8
+  for (int n = 0; n < NFFT; ++n) {
+    const int j = (k * n) & (NFFT - 1);
+    re = fma(s_x[n], s_c[j], re);
+    im = fma(s_x[n], s_s[j], im);
+  }
+  mag[(size_t)blockIdx.x * ldmag + k] = (float)sqrt(re * re + im * im);
+}
+
+// mel filterbank -> log(clip(., 1e-5)) / coef  (dvae.py:199-206,267-268), one frame per block.  mag [F, ldmag];
+// fb [nbin][MELP] (bin-major, mel padded with zero columns); out time-major [F, MELP], pad channels written as 0.
 template <int MELP>
-__global__ void __launch_bounds__(MELP) k_mel_log(const float* __restrict__ spec, int ldspec, int nbin,
+__global__ void __launch_bounds__(MELP) k_mel_log(const float* __restrict__ mag, int ldmag, int nbin,
                                                    const float* __restrict__ fb, const float* __restrict__ coef, int n_mels,
                                                    float* __restrict__ out) {
   extern __shared__ float s_mag[];
-  const float* row = spec + (size_t)blockIdx.x * ldspec;
-  for (int k = threadIdx.x; k < nbin; k += MELP) {
-    const float re = row[2 * k], im = row[2 * k + 1];
-    s_mag[k] = sqrtf(fmaf(re, re, im * im));
-  }
+  const float* row = mag + (size_t)blockIdx.x * ldmag;
+  for (int k = threadIdx.x; k < nbin; k += MELP) s_mag[k] = row[k];
   __syncthreads();
   const int m = threadIdx.x;
   float a = 0.f;

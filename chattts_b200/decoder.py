@@ -208,7 +208,7 @@ class TokenDecoder:
 
 # ---------------------------------------------------------------------------------------------------------------------
 # DVAE encode branch (speaker enrolment): wav -> codes.  dvae.py:175-206,231-236,265-274,102-128.
-ENC_NFFT, ENC_HOP, ENC_SPEC_K, ENC_SR = 1024, 256, 1056, 24000   # MelSpectrogramFeatures defaults (dvae.py:176-181)
+ENC_NFFT, ENC_HOP, ENC_SR = 1024, 256, 24000   # MelSpectrogramFeatures defaults (dvae.py:176-181)
 
 
 def mel_filterbank(n_freqs: int = ENC_NFFT // 2 + 1, n_mels: int = MEL, sample_rate: int = ENC_SR) -> torch.Tensor:
@@ -225,25 +225,13 @@ def mel_filterbank(n_freqs: int = ENC_NFFT // 2 + 1, n_mels: int = MEL, sample_r
     return torch.clamp(torch.min(down, up), min=0.0)
 
 
-def dft_basis(n_fft: int = ENC_NFFT, spec_k: int = ENC_SPEC_K, window: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Windowed forward real DFT as GEMM weights [spec_k, n_fft]: row 2k = hann[n] cos(2 pi k n / N), row 2k+1 =
-    -hann[n] sin(2 pi k n / N) (periodic Hann, ``torch.stft`` / torchaudio ``Spectrogram`` defaults); zero pad rows."""
-    n = torch.arange(n_fft, dtype=torch.float64)[None, :]
-    k = torch.arange(n_fft // 2 + 1, dtype=torch.float64)[:, None]
-    ang = 2 * math.pi * ((n * k) % n_fft) / n_fft
-    w = (torch.hann_window(n_fft, periodic=True, dtype=torch.float64) if window is None else window.double().cpu())[None, :]
-    basis = torch.zeros(spec_k, n_fft, dtype=torch.float64)
-    basis[0: 2 * (n_fft // 2 + 1): 2] = torch.cos(ang) * w
-    basis[1: 2 * (n_fft // 2 + 1): 2] = -torch.sin(ang) * w
-    return basis.float()
-
-
 def pack_dvae_encoder(s: State, stack: ConvStackConfig, dim: int, vq: VQConfig) -> torch.Tensor:
     """Blob of ``ctb_dvae_encoder_create`` (order of decoder_api.cu::enc_layout)."""
     assert stack.idim == dim and stack.odim == vq.dim, "encoder stack must map DVAE dim -> vq dim"
     pk = _Packer()
     # a real checkpoint carries torchaudio's buffers (window, filterbank); the synthetic states do not
-    pk.add(dft_basis(window=s.get("preprocessor_mel.mel_spec.spectrogram.window")))
+    window = s.get("preprocessor_mel.mel_spec.spectrogram.window")
+    pk.add(torch.hann_window(ENC_NFFT) if window is None else window)
     fb = s.get("preprocessor_mel.mel_spec.mel_scale.fb")
     fb = mel_filterbank() if fb is None else fb.detach().float().cpu()
     pk.add(torch.cat([fb, torch.zeros(fb.shape[0], MEL_PAD - MEL)], 1))

@@ -207,7 +207,7 @@ int ctb_vocos_decode(ctb_decoder* h, const float* mel_dev, int32_t B, int32_t F,
  * (dvae.py:102-128).  Caller: Chat.sample_audio_speaker (core.py:179-180) and the automatic speaker sample of
  * multi-sentence infer() (core.py:435-453).
  * cfg: idim = DVAE dim (512), odim = vq_dim (1024), hidden / n_layer / bn_dim / kernel / dilation of the encoder stack,
- * vq_* as for the decoder.  The blob holds the windowed DFT basis, the mel filterbank, coef, the two downsample convs,
+ * vq_* as for the decoder.  The blob holds the analysis window, the mel filterbank, coef, the two downsample convs,
  * the stack and the FSQ project_in matrices (order: chattts_b200/decoder.py::pack_dvae_encoder). */
 typedef struct ctb_encoder ctb_encoder;
 int64_t ctb_dvae_encoder_blob_floats(const ctb_convstack_config* enc_cfg);

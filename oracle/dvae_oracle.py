@@ -106,12 +106,21 @@ def decode_to_wavs(results, use_decoder: bool, dec_state: State, vocos_state: St
 # encode branch (speaker enrolment): DVAE.forward(mode="encode"), dvae.py:265-274
 
 
-def mel_features(wav: torch.Tensor, n_fft: int = 1024, hop: int = 256, n_mels: int = 100, sr: int = 24000) -> torch.Tensor:
+def mel_features(wav: torch.Tensor, n_fft: int = 1024, hop: int = 256, n_mels: int = 100, sr: int = 24000,
+                 precise_stft: bool = False) -> torch.Tensor:
     """MelSpectrogramFeatures.forward (dvae.py:199-206) = log(clip(MelSpectrogram(power=1, center)(wav), 1e-5)).
     [3p] torchaudio: |stft| with a periodic Hann window and reflect padding, then the HTK triangular filterbank
-    (norm=None, f_min 0, f_max sr/2).  wav [L] -> [n_mels, L // hop + 1]."""
-    spec = torch.stft(wav, n_fft, hop, n_fft, torch.hann_window(n_fft), center=True, pad_mode="reflect", normalized=False,
-                      onesided=True, return_complex=True).abs()
+    (norm=None, f_min 0, f_max sr/2).  wav [L] -> [n_mels, L // hop + 1].
+    ``precise_stft`` evaluates the same |STFT| (fp32 samples, fp32 window) in float64 and rounds the magnitude to fp32:
+    the value the reference's fp32 FFT approximates.  The log amplifies the FFT's rounding error in bins far below the
+    frame's peak, so two correct fp32 implementations disagree there; the precise form is what the GPU path is held to."""
+    win = torch.hann_window(n_fft)
+    if precise_stft:
+        spec = torch.stft(wav.double(), n_fft, hop, n_fft, win.double(), center=True, pad_mode="reflect", normalized=False,
+                          onesided=True, return_complex=True).abs().float()
+    else:
+        spec = torch.stft(wav, n_fft, hop, n_fft, win, center=True, pad_mode="reflect", normalized=False,
+                          onesided=True, return_complex=True).abs()
     n_freqs = n_fft // 2 + 1
     all_freqs = torch.linspace(0, sr // 2, n_freqs)
     m_pts = torch.linspace(0.0, 2595.0 * math.log10(1.0 + (sr / 2.0) / 700.0), n_mels + 2)
@@ -157,9 +166,9 @@ def fsq_quantize(x: torch.Tensor, s: State, G: int = 2, R: int = 2, levels=(5, 5
 
 
 def dvae_encode(wav: torch.Tensor, s: State, *, n_layer: int = 12, dilation: int = 2, scale_base: int = 4,
-                bound_input: bool = True, return_parts: bool = False):
+                bound_input: bool = True, return_parts: bool = False, precise_stft: bool = False):
     """DVAE.forward(mode='encode') (dvae.py:265-274): wav [L] -> ids [1, G*R, T]."""
-    mel = mel_features(wav) / s["coef"].view(100, 1)
+    mel = mel_features(wav, precise_stft=precise_stft) / s["coef"].view(100, 1)
     x = F.gelu(F.conv1d(mel[None], s["downsample_conv.0.weight"], s["downsample_conv.0.bias"], padding=1))
     x = F.gelu(F.conv1d(x, s["downsample_conv.2.weight"], s["downsample_conv.2.bias"], stride=2, padding=1))
     y = F.gelu(F.conv1d(x, s["encoder.conv_in.0.weight"], s["encoder.conv_in.0.bias"], padding=1))

@@ -4,7 +4,10 @@
 
 Codes are integers: the bar is bit-exact.  Each index is a rounding of a float, so a mismatch is only tolerated where the
 oracle's own decision margin (distance of the pre-rounding value to the rounding edge) is inside fp32 reordering noise
-(< 1e-3); the fixture was chosen with every margin >= 9e-3, so there the comparison is exact with no exceptions."""
+(< 1e-3); the fixture was chosen with every margin >= 9e-3, so there the comparison is exact with no exceptions.
+The GPU evaluates |STFT| as a float64 DFT (correctly rounded magnitudes); the oracle is run with ``precise_stft=True``
+for the live comparison, while the fixture carries the reference's fp32-FFT mel - whose rounding error the log amplifies
+in the bins far below a frame's peak, hence the linear-domain mel comparison and the looser margin tolerance there."""
 import os
 
 import numpy as np
@@ -17,6 +20,18 @@ from chattts_b200.synth import synth_all, synth_dvae_state, synth_speech_like
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 _e = {}
+
+
+def assert_mel_close(logmel_over_coef: torch.Tensor, ref: torch.Tensor, coef: torch.Tensor):
+    """Compare in the LINEAR mel domain: an fp32 FFT and an fp32 DFT-as-GEMM both carry an absolute error of ~1e-6 of the
+    frame's peak, which the log turns into a large difference wherever a mel bin is far below that peak."""
+    a = torch.exp(logmel_over_coef.double().cpu() * coef.double().view(-1, 1))
+    b = torch.exp(ref.double().cpu() * coef.double().view(-1, 1))
+    tol = 2e-5 * b.amax(dim=0, keepdim=True) + 2e-6
+    assert bool(((a - b).abs() <= tol).all()), float(((a - b).abs() / tol).max())
+    big = b > 1e-2 * b.amax(dim=0, keepdim=True)            # bins that matter: log-domain agreement
+    assert float((logmel_over_coef.cpu() - ref.cpu()).abs()[big].max()) < 2e-3
+
 
 
 def _state():
@@ -43,10 +58,10 @@ def test_encode_matches_the_reference_generated_fixture_exactly():
     wav = synth_speech_like(float(z["seconds"]), int(z["seed"]))
     ids, mel, margin = enc.encode(wav, want_mel=True, want_margin=True)
     assert tuple(ids.shape) == tuple(z["ids"].shape[1:]) and ids.dtype == torch.int32
-    assert np.abs(mel.cpu().numpy() - z["mel_over_coef"]).max() < 1e-3          # log-mel / coef, values span -23 .. 7
     assert float(z["margin"].min()) > 5e-3
     assert np.array_equal(ids.cpu().numpy(), z["ids"][0])
-    assert np.abs(margin.cpu().numpy() - z["margin"][0]).max() < 1e-3
+    assert np.abs(margin.cpu().numpy() - z["margin"][0]).max() < 2e-2      # fp32-FFT noise of the reference mel
+    assert_mel_close(mel, torch.from_numpy(z["mel_over_coef"]), _state()["coef"].reshape(-1))
 
 
 @pytest.mark.parametrize("seconds,seed", [(0.55, 2), (2.0, 1), (3.013, 5)])
@@ -56,13 +71,15 @@ def test_encode_matches_oracle_on_other_lengths(seconds, seed):
     enc, st = encoder()
     wav = synth_speech_like(seconds, seed)
     ids, mel, margin = enc.encode(wav, want_mel=True, want_margin=True)
-    ref_ids, ref_margin, ref_mel, _ = dvae_encode(wav, st, return_parts=True)
+    ref_ids, ref_margin, ref_mel, _ = dvae_encode(wav, st, return_parts=True, precise_stft=True)
     F = wav.numel() // 256 + 1
     assert tuple(ids.shape) == (4, F // 2) == tuple(ref_ids.shape[1:])
-    assert (mel.cpu() - ref_mel).abs().max() < 1e-3
     same = ids.cpu() == ref_ids[0].int()
     assert bool(same[ref_margin[0] > 1e-3].all()), "an index with a clear decision margin differs from the oracle"
     assert float(same.float().mean()) > 0.99
+    assert float((margin.cpu() - ref_margin[0]).abs().max()) < 2e-3
+    assert_mel_close(mel, ref_mel, st["coef"].reshape(-1))
+    assert float((mel.cpu() - ref_mel).abs().max()) < 2e-3        # against the precise oracle the LOG mel agrees everywhere
 
 
 def test_fma_twin_gives_the_same_codes(monkeypatch):
