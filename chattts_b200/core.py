@@ -45,25 +45,24 @@ class Chat:
     # ------------------------------------------------------------------ loading
     def load(self, source="local", force_redownload=False, compile: bool = False, custom_path=None,
              device: Optional[torch.device] = None, coef: Optional[torch.Tensor] = None, use_flash_attn=False,
-             use_vllm=False, experimental: bool = False) -> bool:
+             use_vllm=False, experimental: bool = False, spk_stat: Optional[str] = None) -> bool:
         """core.py:137-163.  ``compile`` / ``use_flash_attn`` / ``use_vllm`` / ``experimental`` are accepted and
-        ignored (one back end).  Asset discovery, tokenizer, the homophone map and speaker come
-        from the reference package, which must be importable; weights go through the reference's own loaders
-        (safetensors + ``LlamaModel.from_pretrained``)."""
-        try:
-            import ChatTTS as ref  # the reference package (out-of-scope host components)
-        except Exception as e:  # pragma: no cover - needs the reference + assets
-            raise RuntimeError("Chat.load() needs the reference `ChatTTS` package for asset download, tokenizer "
-                               "and speaker handling; use Chat.load_states() for in-memory weights") from e
-        from dataclasses import asdict
-
-        helper = ref.Chat(self.logger)
-        root = helper.download_models(source, force_redownload, custom_path)
+        ignored (one back end).  The asset files are located like the reference does for
+        ``source="local"`` (working directory or ``custom_path``) and ``"custom"``; downloading / sha256 checking
+        (core.py:66-135) is left to the reference package, which ``source="huggingface"`` therefore still needs.
+        ``spk_stat`` (config.py:132, the base16384 std|mean table random speakers are drawn from) is taken from the
+        argument, else from an importable reference package; without it only ``sample_random_speaker`` is unavailable."""
+        root = self.download_models(source, force_redownload, custom_path)
         if root is None:
             return False
-        paths = {k: os.path.join(root, v) for k, v in asdict(helper.config.path).items()}
+        from dataclasses import asdict
+
+        paths = {k: os.path.join(root, v) for k, v in asdict(self.config.path).items()}
         from safetensors.torch import load_file
         from transformers import LlamaModel
+
+        from .speaker import Speaker
+        from .tokenizer import Tokenizer
 
         gpt_model = LlamaModel.from_pretrained(paths["gpt_ckpt_path"])
         states = {
@@ -71,14 +70,38 @@ class Chat:
             "embed": load_file(paths["embed_path"]), "decoder": load_file(paths["decoder_ckpt_path"]),
             "dvae": load_file(paths["dvae_ckpt_path"]), "vocos": load_file(paths["vocos_ckpt_path"]),
         }
-        from ChatTTS.model import Speaker, Tokenizer
+        homophones = None
+        if spk_stat is None or homophones is None:
+            try:
+                import ChatTTS as ref  # optional: only its data constants are read
 
+                spk_stat = spk_stat or ref.config.Config().spk_stat
+                cand = os.path.join(os.path.dirname(ref.__file__), "res", "homophones_map.json")   # core.py:39-42
+                homophones = cand if os.path.exists(cand) else None
+            except Exception:
+                pass
         dev = device or torch.device("cuda")
-        homophones = os.path.join(os.path.dirname(ref.__file__), "res", "homophones_map.json")   # core.py:39-42
-        self.normalizer = Normalizer(homophones if os.path.exists(homophones) else None, self.logger)
+        self.normalizer = Normalizer(homophones, self.logger)
         return self.load_states(states, tokenizer=Tokenizer(paths["tokenizer_path"]),
-                                speaker=Speaker(self.config.gpt.hidden_size, helper.config.spk_stat, dev), device=dev,
-                                coef=coef)
+                                speaker=Speaker(self.config.gpt.hidden_size, spk_stat, dev), device=dev, coef=coef)
+
+    def download_models(self, source="local", force_redownload=False, custom_path=None) -> Optional[str]:
+        """core.py:66-135, without the downloader: returns the folder that holds ``asset/`` or ``None``."""
+        if source == "huggingface":
+            try:
+                import ChatTTS as ref
+            except Exception as e:  # pragma: no cover - needs the reference + network
+                raise RuntimeError('source="huggingface" downloads through the reference package, which is not '
+                                   'installed; fetch the assets yourself and use source="custom"') from e
+            return ref.Chat(self.logger).download_models(source, force_redownload, custom_path)
+        root = custom_path if custom_path is not None else os.getcwd()
+        from dataclasses import asdict
+
+        missing = [v for v in asdict(self.config.path).values() if not os.path.exists(os.path.join(root, v))]
+        if missing:
+            self.logger.error("assets missing under %s: %s", root, ", ".join(missing))
+            return None
+        return str(root)
 
     def load_states(self, states: Dict[str, Dict[str, torch.Tensor]], tokenizer, speaker, device=None, coef=None,
                     max_batch: int = 32, max_context: int = 4096, weights_blob: Optional[torch.Tensor] = None) -> bool:
@@ -189,10 +212,12 @@ class Chat:
             text = [text]
         text = [self.normalizer(t, do_text_normalization, do_homophone_replacement, lang) for t in text]
         if not skip_refine_text:
-            refined = self._refine_text(text, self.device, params_refine_text)
-            tokens = [i[i.less(self.tokenizer.break_0_ids)] for i in refined.ids]
+            tokens = []
+            for lo in range(0, len(text), self.gpt.max_batch):          # one batch in the reference; chunks beyond max_batch
+                refined = self._refine_text(text[lo: lo + self.gpt.max_batch], self.device, params_refine_text)
+                tokens += [i[i.less(self.tokenizer.break_0_ids)] for i in refined.ids]
+                refined.destroy()
             text = self.tokenizer.decode(tokens)
-            refined.destroy()
             if refine_text_only:
                 if split_text and isinstance(text, list):
                     text = "\n".join(text)
@@ -213,7 +238,10 @@ class Chat:
         if split_text:
             n = (len(text) + max_split_batch - 1) // max_split_batch
         else:
-            n, max_split_batch = 1, len(text)
+            # the reference runs all texts as one batch; batches beyond the handle's max_batch run as consecutive chunks
+            # (rows are independent, so the result per text is the same; noise rows restart per chunk)
+            max_split_batch = min(len(text), self.gpt.max_batch)
+            n = (len(text) + max_split_batch - 1) // max_split_batch
         for i in range(n):
             chunk = text[i * max_split_batch: (i + 1) * max_split_batch]
             for result in self._infer_code(chunk, stream, self.device, use_decoder, params_infer_code):

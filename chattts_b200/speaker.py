@@ -20,13 +20,16 @@ _LZMA = dict(format=lzma.FORMAT_RAW, filters=[{"id": lzma.FILTER_LZMA2, "preset"
 
 
 class Speaker:
-    def __init__(self, dim: int, spk_cfg: str, device=torch.device("cpu")) -> None:
+    def __init__(self, dim: int, spk_cfg: Optional[str], device=torch.device("cpu")) -> None:
+        self.dim = dim
+        self.std = self.mean = None
+        if spk_cfg is None:          # no statistics: everything but random sampling works
+            return
         stat = np.frombuffer(b14.decode_from_string(spk_cfg), dtype=np.float16).copy()
         if stat.size != 2 * dim:
             raise ValueError(f"spk_stat holds {stat.size} values, expected std|mean of width {dim}")
         spk_stat = torch.from_numpy(stat).to(device=device)
         self.std, self.mean = spk_stat.chunk(2)
-        self.dim = dim
 
     # ------------------------------------------------------------------ sampling / strings
     def sample_random(self) -> str:
@@ -34,6 +37,8 @@ class Speaker:
 
     @torch.no_grad()
     def _sample_random(self) -> torch.Tensor:
+        if self.std is None:
+            raise RuntimeError("this Speaker was built without spk_stat (config.py:132): pass it to Chat.load(spk_stat=...)")
         return torch.randn(self.dim, device=self.std.device, dtype=self.std.dtype).mul_(self.std).add_(self.mean)
 
     @staticmethod

@@ -81,3 +81,18 @@ def test_streaming_windows_equal_the_cumulative_redecode():
         assert x.shape == y.shape and np.abs(x - y).max() <= 1e-6
     # the final block drops all-silent columns (|x| <= 1e-5 in every row): compare what both kept
     assert abs(fast[-1].shape[1] - slow[-1].shape[1]) <= 2
+
+
+def test_more_texts_than_max_batch_run_as_chunks():
+    """split_text=False with more texts than the handle's max_batch (4 here) must not raise; rows are
+    independent, so the first chunk's waveforms equal a run of just those texts."""
+    c = chat()
+    texts = ["one", "two two", "three", "four", "five five", "six"]
+    p = c.InferCodeParams(manual_seed=3, max_new_token=24, min_new_token=24, show_tqdm=False)
+    out = c.infer(list(texts), skip_refine_text=True, split_text=False, params_infer_code=p)
+    first = c.infer(list(texts[:4]), skip_refine_text=True, split_text=False, params_infer_code=p)
+    assert len(out) == 6 and all(w.size > 0 for w in out)
+    assert all(np.array_equal(a, b) for a, b in zip(out[:4], first))
+    r = c.RefineTextParams(manual_seed=5, max_new_token=8, show_tqdm=False)
+    refined = c.infer(list(texts), refine_text_only=True, split_text=False, params_refine_text=r)
+    assert isinstance(refined, list) and len(refined) == 6
