@@ -342,9 +342,9 @@ def bench_decoder(dev, B: int = 64, T: int = 469):
 DEC_B, DEC_T = 64, 469                      # BASELINE configs[3]: 64 utterances of 10 s (469 tokens = 938 mel frames)
 DEC_FLOP_PER_FRAME = 78.7e6                 # hidden path, decoder 25.86 + vocos 13.50 + iDFT MMAC per frame
 DEC_ALGO_BYTES = 92.2e6 + 157.8e6 + 61.4e6  # hiddens in + fp32 weights + waveform out
-# dram__bytes_read + dram__bytes_write of one tokens_to_wav call at C4 from the ncu launch list of this round
-# (profiles/r02_decoder_c4_launches_summary.txt); a constant from that capture
-DEC_TRAFFIC_C4 = None
+# dram__bytes_read + dram__bytes_write summed over the 70 launches of one tokens_to_wav call at C4, from the ncu capture of
+# this round (tools/dec_profile.py -> profiles/r02_decoder_c4_dram.csv, _summary.txt); a constant from that capture
+DEC_TRAFFIC_C4 = 30_021_370_111
 
 
 def measured_tf32_peak(dev):
@@ -503,6 +503,9 @@ def run_decoder(args, rank: int, world: int, local_rank: int):
                              "per algorithmic MAC, so the tensor pipes do 3x this figure",
                      "tensor_work_frac": round(3 * ach / tf32_peak, 4),
                      "hbm": {"algorithmic_bytes": int(DEC_ALGO_BYTES), "achieved_gbs": round(DEC_ALGO_BYTES / (ms / 1e3) / 1e9, 1),
+                             "dram_traffic_gbs": round(DEC_TRAFFIC_C4 / (ms / 1e3) / 1e9, 1),
+                             "traffic_note": "traffic = ncu dram bytes of one call (constant from profiles/r02_decoder_c4_dram.csv), "
+                                             "96x the algorithmic bytes: the 4x-wide ConvNeXt intermediates round-trip HBM",
                              "peak_gbs": hbm_peak, "peak_source": hbm_src},
                      "fma_twin_ms": None if fma_ms is None else round(fma_ms, 2)},
         "cpu_baseline": cpu,
