@@ -207,7 +207,12 @@ k_tc_gemm(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
 // in L2) with TWO TMEM accumulators: warps 6-9 run the epilogue of tile i while warps 0-5 already feed tile i+1's
 // mainloop.  k_tc_gemm paid, per 128x128 tile, TMEM alloc + barrier init + a serial epilogue (bias / erf-GELU / stores of
 // 64 KB) behind a mainloop that is only 8 k-steps long for the ConvNeXt pw1 GEMMs (K = 256) - ncu at BASELINE configs[3]:
-// pw1 23.2 ms vs pw2 15.8 ms for the same flops (profiles/r02_decoder_c4_dram_summary.txt).
+// pw1 23.2 ms vs pw2 15.8 ms for the same flops (profiles/r02_decoder_c4_dram_summary.txt).  C4: 43.3 -> 33.8 ms.
+// Tried on top and rejected (measured): loading W as fp32 and splitting it hi / lo in the worker warps like A (no weight
+// copies in HBM, 32 instead of 48 KB per k-step from L2) - 41.9 ms.  The k-step is shared-memory-bandwidth bound: TMA
+// writes + split reads / writes + the operand reads of 12 MMAs were 192 KB per k-step and became 224 KB, against
+// ~158 KB that 128 B/clk deliver in the 0.65 us the MMAs take.  Less shared-memory traffic per MMA (operands pre-split by
+// their producer, or A from TMEM) is what would lift this kernel further.
 constexpr int TCP_THREADS = 320;
 
 __device__ __forceinline__ void mbar_wait_or_trap(uint64_t* bar, uint32_t parity) {
@@ -379,7 +384,7 @@ template <int EPI>
 inline int tc_gemm_launch(cudaStream_t s, const float* A, int lda, int B, int F, int N, int K, int taps, int Cin, int dil,
                           int pad, const float* W_hi, const float* W_lo, const float* bias, const float* gamma,
                           const float* res, int ldres, float* C, int ldc) {
-  static const bool persistent = getenv("CTB_TC_NONPERSISTENT") == nullptr;
+  const bool persistent = getenv("CTB_TC_NONPERSISTENT") == nullptr;   // the one-tile-per-CTA twin stays for cross-checks
   { int arc = persistent ? ensure_smem_attr((const void*)k_tc_gemm_p<EPI>, TC_SMEM_BYTES)
                          : ensure_smem_attr((const void*)k_tc_gemm<EPI>, TC_SMEM_BYTES); if (arc) return arc; }
   CUtensorMap ma, mh, ml;

@@ -202,3 +202,25 @@ def test_windowed_decode_equals_slices_of_the_full_decode(use_decoder):
         assert win.shape == (3, b - a)
         ref = full[:, a:b]
         assert np.abs(win - ref).max() <= 1e-6 * max(1.0, float(np.abs(ref).max())) + 1e-9, (a, b, float(np.abs(win - ref).max()))
+
+
+def test_persistent_gemm_equals_the_one_tile_per_cta_twin_bit_for_bit():
+    """k_tc_gemm_p (persistent CTAs, two TMEM accumulators, weights split hi/lo on the fly) runs the same MMAs in the same
+    order as k_tc_gemm (CTB_TC_NONPERSISTENT=1: one tile per CTA, pre-split weight copies): identical mel and waveform."""
+    import os
+
+    from chattts_b200.decoder import DVAE, Vocos
+
+    m = models()
+    x = torch.randn(3, 301, 768, generator=torch.Generator().manual_seed(4))      # 602 frames: a partial last M tile
+    wav_p = m["dec"].engine.tokens_to_wav(x, 1)
+    mel_p = m["dec"].engine.dvae_decode(x, 1)
+    os.environ["CTB_TC_NONPERSISTENT"] = "1"
+    try:
+        voc = Vocos(CFG.vocos, "cuda", max_batch=3, max_tokens=301).load_state_dict(m["vs"])
+        dec = DVAE(CFG.decoder, dim=384, device="cuda", vocos=voc, max_batch=3, max_tokens=301).load_state_dict(m["ds"])
+        wav_t = dec.engine.tokens_to_wav(x, 1)
+        mel_t = dec.engine.dvae_decode(x, 1)
+    finally:
+        del os.environ["CTB_TC_NONPERSISTENT"]
+    assert torch.equal(mel_p, mel_t) and torch.equal(wav_p, wav_t)
