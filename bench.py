@@ -344,7 +344,7 @@ DEC_FLOP_PER_FRAME = 78.7e6                 # hidden path, decoder
 DEC_ALGO_BYTES = 92.2e6 + 157.8e6 + 61.4e6  # hiddens in + fp32 weights + waveform out
 # dram__bytes_read + dram__bytes_write summed over the 70 launches of one tokens_to_wav call at C4, from the ncu capture of
 # this round (tools/dec_profile.py -> profiles/r02_decoder_c4_dram.csv, _summary.txt); a constant from that capture
-DEC_TRAFFIC_C4 = 30_021_370_111
+DEC_TRAFFIC_C4 = 29_863_704_832
 
 
 def measured_tf32_peak(dev):
@@ -495,7 +495,7 @@ def run_decoder(args, rank: int, world: int, local_rank: int):
                 "h2d_bytes_per_step": int(x_host.numel() * 4), "d2h_bytes_per_step": int(wav_host.numel() * 4),
                 "ms_per_step": round(ms_e2e, 3)},
         "gpu_launches": launches, "clocks": clk.summary(),
-        "roofline": {"bound": "tensor", "kernel": "k_tc_gemm<EPI> (tcgen05 3xTF32 conv-as-GEMM; 46 of the call's launches, >90 % of its time)",
+        "roofline": {"bound": "tensor", "kernel": "k_tc_gemm_p<EPI> (persistent tcgen05 3xTF32 conv-as-GEMM, two TMEM accumulators; 47 of the call's 70 launches, 94 % of its time)",
                      "achieved": round(ach, 1), "peak": round(tf32_peak, 1), "unit": "TFLOP/s", "frac": round(ach / tf32_peak, 4),
                      "traffic": DEC_TRAFFIC_C4,
                      "peak_source": "measured in this run: torch.matmul fp32 8192^3 with allow_tf32 (cuBLAS TF32), best of 5",
