@@ -141,7 +141,7 @@ def fsq_bound(z: torch.Tensor, levels: torch.Tensor, eps: float = 1e-3) -> torch
 
 
 def fsq_quantize(x: torch.Tensor, s: State, G: int = 2, R: int = 2, levels=(5, 5, 5, 5), scale_base: int = 4,
-                 bound_input: bool = True):
+                 bound_input: bool = True, return_quantized: bool = False):
     """[3p] GFSQ.forward (dvae.py:102-128) -> GroupedResidualFSQ.forward: x [B, T, dim] -> (ids [B, G*R, T], margin).
     Per group: project_in, then R stages of ``q = round(bound(res / s_r))``, ``res -= q / (levels // 2) * s_r`` with
     ``s_r = scale_base ** -r``; index = sum_k (q_k + levels_k // 2) * prod(levels[:k]).  ``bound_input`` applies bound()
@@ -151,17 +151,22 @@ def fsq_quantize(x: torch.Tensor, s: State, G: int = 2, R: int = 2, levels=(5, 5
     lv = torch.tensor(levels)
     basis = torch.cumprod(torch.tensor([1] + list(levels[:-1])), 0)
     half_w = (lv // 2).float()
-    ids, margins = [], []
+    ids, margins, zq = [], [], []
     for g, xg in enumerate(x.chunk(G, dim=-1)):
         z = F.linear(xg, s[f"vq_layer.quantizer.rvqs.{g}.project_in.weight"], s[f"vq_layer.quantizer.rvqs.{g}.project_in.bias"])
         res = fsq_bound(z, lv) if bound_input else z
+        acc = torch.zeros_like(res)
         for r in range(R):
             sc = float(scale_base) ** -r
             bz = fsq_bound(res / sc, lv)
             q = torch.round(bz)
             margins.append((0.5 - (bz - q).abs()).amin(dim=-1))
             res = res - (q / half_w) * sc
+            acc = acc + (q / half_w) * sc
             ids.append(((q + half_w).long() * basis).sum(-1))
+        zq.append(acc)
+    if return_quantized:
+        return torch.stack(ids, dim=1), torch.stack(margins, dim=1), zq
     return torch.stack(ids, dim=1), torch.stack(margins, dim=1)
 
 
