@@ -40,3 +40,14 @@ def test_layout_query_matches_parameter_count():
 def test_sampler_config_struct_size_matches_header():
     # 8 floats + float + 3 ints + 1 int + 32 floats + 5 ints + float + int (ABI v2) + pad + u64
     assert ctypes.sizeof(_lib.SamplerConfig) == 8 * 4 + 4 + 4 + 4 + 4 + 32 * 4 + 4 * 5 + 4 + 4 + 4 + 8
+
+
+def test_graft_entry_build_runs_on_cpu():
+    """The driver calls __graft_entry__.build() in the build container every round: it must compile, load and agree with
+    the header's ABI version (a hard-coded version there went stale once)."""
+    import importlib
+    import sys
+
+    sys.path.insert(0, ROOT)
+    entry = importlib.import_module("__graft_entry__")
+    entry.build()
